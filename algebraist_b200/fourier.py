@@ -1,0 +1,198 @@
+"""Drop-in for `algebraist.fourier`: sn_fft, sn_ifft, slow_sn_ft, slow_sn_ift.
+
+Same signatures, dict[partition -> tensor] layout, key order and shape quirks
+as the reference (/root/reference/src/algebraist/fourier.py); the arithmetic
+runs in hand-written sm_100a CUDA kernels behind the C ABI of include/snfft.h.
+There is no CPU path: CPU tensors are copied to the current CUDA device,
+transformed there and copied back."""
+import math
+
+import torch
+
+from . import _lib
+from .plan import get_plan
+
+# The reference switches to its dense path at n <= BASE_CASE (fourier.py:27);
+# the only observable effect kept here is the `.squeeze()` it applies there
+# (fourier.py:129), which collapses size-1 leading dimensions for d > 1.
+BASE_CASE = 5
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _device_ctx(device):
+    return torch.cuda.device(device)
+
+
+def _to_device(t: torch.Tensor):
+    """Returns (cuda tensor, original device)."""
+    if t.is_cuda:
+        return t, t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("algebraist_b200 needs a CUDA device (there is no CPU fallback)")
+    return t.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=False), t.device
+
+
+def _forward_packed(f2d: torch.Tensor, n: int):
+    """f2d: (B, n!) contiguous CUDA tensor -> (plan, packed coefficients (B * n!,))."""
+    plan = get_plan(n, f2d.dtype, f2d.device)
+    batch = f2d.shape[0]
+    packed = torch.empty(batch * plan.nfact, dtype=f2d.dtype, device=f2d.device)
+    if batch:
+        with _device_ctx(f2d.device):
+            ws = plan.workspace(batch)
+            _lib.check(_lib.load().snfft_forward(plan.handle, f2d.data_ptr(), batch, packed.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _stream_ptr(f2d.device)),
+                       "snfft_forward")
+    return plan, packed
+
+
+def _inverse_packed(plan, packed: torch.Tensor, batch: int) -> torch.Tensor:
+    out = torch.empty((batch, plan.nfact), dtype=packed.dtype, device=packed.device)
+    if batch:
+        with _device_ctx(packed.device):
+            ws = plan.workspace(batch)
+            _lib.check(_lib.load().snfft_inverse(plan.handle, packed.data_ptr(), batch, out.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _stream_ptr(packed.device)),
+                       "snfft_inverse")
+    return out
+
+
+def _check_input(fn_vals, n):
+    if not isinstance(fn_vals, torch.Tensor):
+        raise TypeError("fn_vals must be a torch.Tensor")
+    if not isinstance(n, int) or n < 2:
+        raise ValueError(f"n must be an integer >= 2, got {n!r}")
+    if fn_vals.dim() < 1 or fn_vals.shape[-1] != math.factorial(n):
+        raise ValueError(f"last dimension of fn_vals must be n! = {math.factorial(n)}, got shape {tuple(fn_vals.shape)}")
+    if fn_vals.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"only float32 and float64 are supported, got {fn_vals.dtype}")
+
+
+def sn_fft(fn_vals: torch.Tensor, n: int, verbose: bool = False) -> dict:
+    """Fast Fourier transform on S_n (reference fourier.py:281-288).
+
+    fn_vals: (n!,) or (..., n!) values of f in lexicographic order of one-line
+    permutations.  Returns {partition: F(partition)} in generate_partitions(n)
+    order; 1-dimensional irreps have the leading shape, the others
+    leading + (d, d).  For n <= 5 the reference squeezes size-1 leading
+    dimensions of the d > 1 entries (fourier.py:129); that is reproduced."""
+    _check_input(fn_vals, n)
+    x, home = _to_device(fn_vals)
+    lead = tuple(x.shape[:-1])
+    f2d = x.reshape(-1, x.shape[-1]).contiguous()
+    plan, packed = _forward_packed(f2d, n)
+    batch = f2d.shape[0]
+    result = {}
+    for lam, d, off in zip(plan.partitions, plan.dims, plan.offsets):
+        blk = packed[off * batch:(off + d * d) * batch]
+        if d == 1:
+            val = blk.view(lead)
+        else:
+            val = blk.view(lead + (d, d))
+            if n <= BASE_CASE:
+                val = val.squeeze()
+        result[lam] = val if home == x.device else val.to(home)
+    return result
+
+
+def _pack_ft(ft: dict, n: int):
+    some = next(iter(ft.values()))
+    if not isinstance(some, torch.Tensor):
+        raise TypeError("ft must map partitions to tensors")
+    x, home = _to_device(some)
+    if x.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"only float32 and float64 are supported, got {x.dtype}")
+    plan = get_plan(n, x.dtype, x.device)
+    missing = [p for p in plan.partitions if p not in ft]
+    if missing:
+        raise ValueError(f"ft is missing partitions {missing[:3]}...")
+    triv = ft[plan.partitions[0]]
+    lead = tuple(triv.shape)
+    batch = triv.numel()
+    # zero-copy when ft is the dict sn_fft produced (views into one packed buffer)
+    pieces, contiguous_run, base_ptr = [], True, None
+    for lam, d, off in zip(plan.partitions, plan.dims, plan.offsets):
+        t = ft[lam]
+        if t.numel() != batch * d * d:
+            raise ValueError(f"ft[{lam}] has {t.numel()} elements, expected {batch * d * d}")
+        if not (t.device == x.device and t.dtype == x.dtype and t.is_contiguous()):
+            contiguous_run = False
+        elif base_ptr is None:
+            base_ptr = t.data_ptr()
+            if off != 0:
+                contiguous_run = False
+        elif t.data_ptr() != base_ptr + off * batch * t.element_size():
+            contiguous_run = False
+        pieces.append(t)
+    if contiguous_run and base_ptr is not None:
+        storage_ok = all(p.untyped_storage().data_ptr() == pieces[0].untyped_storage().data_ptr() for p in pieces)
+        if storage_ok:
+            packed = torch.as_strided(pieces[0], (batch * plan.nfact,), (1,), pieces[0].storage_offset())
+            return plan, packed, batch, lead, home
+    packed = torch.cat([p.to(device=x.device, dtype=x.dtype).reshape(-1) for p in pieces])
+    return plan, packed, batch, lead, home
+
+
+def sn_ifft(ft: dict, n: int) -> torch.Tensor:
+    """Inverse fast Fourier transform (reference fourier.py:298-299).
+
+    The reference's recursive inverse raises for n > 5 (fourier.py:202-214);
+    this returns the mathematical inverse
+        f(sigma) = 1/n! sum_lambda d_lambda <F(lambda), rho_lambda(sigma)>
+    at every n, shape leading + (n!,) (squeezed for n <= 5 like the reference)."""
+    plan, packed, batch, lead, home = _pack_ft(ft, n)
+    out = _inverse_packed(plan, packed, batch).view(lead + (plan.nfact,))
+    if n <= BASE_CASE:
+        out = out.squeeze()
+    return out if home == out.device else out.to(home)
+
+
+def _dense_rep(plan, part: int) -> torch.Tensor:
+    d = plan.dims[part]
+    out = torch.empty((plan.nfact, d, d), dtype=plan.dtype, device=plan.device)
+    with _device_ctx(plan.device):
+        _lib.check(_lib.load().snfft_dense_rep(plan.handle, part, out.data_ptr(), _stream_ptr(plan.device)),
+                   "snfft_dense_rep")
+    return out
+
+
+def slow_sn_ft(fn_vals: torch.Tensor, n: int) -> dict:
+    """Dense transform sum_g f(g) rho(g) (reference fourier.py:82-108): the
+    cross-check for sn_fft.  rho_lambda(g) for all g is built on the device
+    from the Young's-orthogonal-form tables (irreps.py:122-148)."""
+    _check_input(fn_vals, n)
+    if fn_vals.dim() > 2:
+        raise ValueError("slow_sn_ft takes (n!,) or (batch, n!) input like the reference")
+    x, home = _to_device(fn_vals)
+    if x.dim() == 1:
+        x = x.unsqueeze(0)                                   # fourier.py:96-97
+    plan = get_plan(n, x.dtype, x.device)
+    results = {}
+    for part, (lam, d) in enumerate(zip(plan.partitions, plan.dims)):
+        mats = _dense_rep(plan, part)
+        if d == 1:
+            res = torch.einsum('bi,i->b', x, mats.view(-1))            # fourier.py:103
+        else:
+            res = torch.einsum('bi,ijk->bjk', x, mats).squeeze()       # fourier.py:105
+        results[lam] = res if home == x.device else res.to(home)
+    return results
+
+
+def slow_sn_ift(ft: dict, n: int) -> torch.Tensor:
+    """Dense inverse (reference fourier.py:302-327), dtype preserving."""
+    some = next(iter(ft.values()))
+    x, home = _to_device(some)
+    plan = get_plan(n, x.dtype, x.device)
+    triv = ft[plan.partitions[0]]
+    lead = tuple(triv.shape)
+    batch = triv.numel()
+    tot = torch.zeros((batch, plan.nfact), dtype=x.dtype, device=x.device)
+    for part, (lam, d) in enumerate(zip(plan.partitions, plan.dims)):
+        mats = _dense_rep(plan, part)
+        blk = ft[lam].to(device=x.device, dtype=x.dtype).reshape(batch, d, d)
+        tot += d * torch.einsum('bij,gij->bg', blk, mats)              # fourier.py:157
+    out = (tot / plan.nfact).view(lead + (plan.nfact,)).squeeze()
+    return out if home == out.device else out.to(home)

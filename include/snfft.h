@@ -1,0 +1,163 @@
+/*
+ * snfft.h -- C ABI of the B200-native S_n fast Fourier transform.
+ *
+ * This is the drop-in boundary for the hot path of dashstander/algebraist
+ * (`sn_fft` / `sn_ifft`, reference src/algebraist/fourier.py).  The reference
+ * is pure Python and has no FFI of its own; each entry point below names the
+ * reference function(s) whose work it replaces.  The Python package
+ * `algebraist_b200` binds this header with ctypes and
+ * re-creates the reference's Python signatures on top of it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary
+ *   - every function returns 0 on success or a negative SNFFT_E* status and
+ *     never throws; snfft_last_error() gives a thread-local message
+ *   - all data pointers are DEVICE pointers unless the name says `_host`
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *     every kernel is launched asynchronously on it, no host synchronisation
+ *   - dtype: 0 = float32, 1 = float64
+ *
+ * Data layout
+ *   function values  f : [B][n!]      row r = f(sigma_r), sigma_r the r-th
+ *                                     permutation of range(n) in lexicographic
+ *                                     order (utils.py:61-63)
+ *   coefficients     F : packed; for each partition lambda in the reference's
+ *                        generate_partitions(n) order (tableau.py:103-123) one
+ *                        contiguous [B][d][d] row-major block that starts at
+ *                        element  B * coef_offset[lambda]   (sum_lambda d^2 = n!)
+ */
+#ifndef SNFFT_H
+#define SNFFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNFFT_OK            0
+#define SNFFT_EINVAL       -1   /* bad argument (n out of range, NULL, bad dtype, B < 0) */
+#define SNFFT_ENOMEM       -2   /* host or device allocation failed                       */
+#define SNFFT_ECUDA        -3   /* a CUDA runtime call or kernel launch failed            */
+#define SNFFT_EWORKSPACE   -4   /* workspace smaller than snfft_workspace_bytes()         */
+#define SNFFT_ENOTSUP      -5   /* valid request this build cannot serve                  */
+
+#define SNFFT_F32 0
+#define SNFFT_F64 1
+
+#define SNFFT_MAX_N 12
+
+typedef struct snfft_plan snfft_plan_t;
+
+/* Library / build identification ("sm_100a" for the product build). */
+const char* snfft_build_info(void);
+
+/* Thread-local description of the last failure on this thread. */
+const char* snfft_last_error(void);
+
+/*
+ * Build the per-n tables once (host combinatorics + device upload).
+ * Replaces, at plan time, everything the reference rebuilds on every call:
+ *   generate_partitions           tableau.py:103-123
+ *   SnIrrep.__init__/dim          irreps.py:40-44, tableau.py:236-265
+ *   split_partition / get_block_indices   irreps.py:64-83
+ *   basis order                   tableau.py:171-198, irreps.py:60-62
+ *   adj_transposition_matrix      irreps.py:91-109  (kept as sparse per-row tables)
+ *   coset_rep_matrices            irreps.py:150-155 (never materialised; words s_i..s_{n-2})
+ * 2 <= n <= SNFFT_MAX_N.  `device` is the CUDA device ordinal.
+ */
+int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out);
+void snfft_plan_destroy(snfft_plan_t* plan);
+
+/*
+ * Plan introspection.  Any out pointer may be NULL.  The returned arrays are
+ * owned by the plan (host memory).
+ *   partitions_flat : [n_partitions][n] rows zero padded, reference order
+ *   dims            : [n_partitions]    d_lambda           (tableau.py:236-265)
+ *   coef_offsets    : [n_partitions+1]  prefix sums of d^2 (last entry = n!)
+ */
+int snfft_plan_info(const snfft_plan_t* plan, int* n, int* dtype, int* n_partitions,
+                    const int32_t** partitions_flat, const int32_t** dims,
+                    const int64_t** coef_offsets);
+
+/*
+ * Table read-back for tests (host arrays owned by the plan):
+ * per-row Young's-orthogonal-form table of s_j = (j j+1) on partition number
+ * `part` of level k (irreps.py:91-109):  rho[t][t] = diag[t],
+ * rho[t][partner[t]] = offdiag[t]  (partner[t] == t when there is none).
+ */
+int snfft_plan_level_info(const snfft_plan_t* plan, int k, int* n_partitions,
+                          const int32_t** partitions_flat, const int32_t** dims);
+int snfft_plan_yor_table(const snfft_plan_t* plan, int k, int part, int j,
+                         int* d, const int32_t** partner, const double** diag,
+                         const double** offdiag);
+
+/* Bytes of device scratch snfft_forward / snfft_inverse need for batch B. */
+size_t snfft_workspace_bytes(const snfft_plan_t* plan, int64_t B);
+
+/*
+ * Forward transform of B functions: F(lambda) = sum_sigma f(sigma) rho_lambda(sigma).
+ * Replaces sn_fft -> fourier_projection -> _fourier_projection /
+ * restrict_to_coset (fourier.py:281-288, 223-278, 111-131, 63-80).
+ */
+int snfft_forward(const snfft_plan_t* plan, const void* f, int64_t B, void* F,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Inverse transform: f(sigma) = (1/n!) sum_lambda d_lambda <F(lambda), rho_lambda(sigma)>.
+ * Replaces sn_ifft -> sn_fourier_decomposition -> inverse_fourier_projection /
+ * _inverse_fourier_projection / lift_from_coset (fourier.py:298-299, 291-295,
+ * 162-219, 134-159, 46-60).  The reference's recursive inverse raises for
+ * n > 5 (fourier.py:202-214); this computes the mathematical inverse at every n.
+ */
+int snfft_inverse(const snfft_plan_t* plan, const void* F, int64_t B, void* f,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Same transforms with HOST buffers (pageable or pinned): copies in, runs the
+ * device pipeline, copies out, and returns after the result is in `F_host` /
+ * `f_host`.  Scratch is owned by the plan and grows on demand.
+ */
+int snfft_forward_host(snfft_plan_t* plan, const void* f_host, int64_t B, void* F_host, void* stream);
+int snfft_inverse_host(snfft_plan_t* plan, const void* F_host, int64_t B, void* f_host, void* stream);
+
+/*
+ * Bit-exact integer kernels.
+ *   perm_rank   : lexicographic rank of m one-line permutations of range(n)
+ *                 (Permutation.permutation_index, permutations.py:187-192)
+ *   perm_unrank : inverse; rows of generate_all_permutations(n) (utils.py:61-63)
+ *   coset_index : ranks of {sigma : sigma[coset] = n-1} in increasing order,
+ *                 (n-1)! entries  == argwhere(sn_perms[:, coset] == n-1)
+ *                 (restrict_to_coset / lift_from_coset, fourier.py:59,79)
+ *   chain_index : for every rank r in [0, n!) the level-1 instance number
+ *                 p_1 = sum_k i_k * n!/k!, i_k = position of value k-1 after the
+ *                 larger values are deleted: the composition of restrict_to_coset
+ *                 over all levels (fourier.py:253), i.e. the input permutation
+ *                 of the fast transform
+ */
+int snfft_perm_rank(int n, const int8_t* perms, int64_t m, int64_t* ranks, void* stream);
+int snfft_perm_unrank(int n, const int64_t* ranks, int64_t m, int8_t* perms, void* stream);
+int snfft_coset_index(int n, int coset, int64_t* idx, void* stream);
+int snfft_chain_index(int n, int64_t* p1_of_rank, void* stream);
+
+/*
+ * Dense representation matrices of partition number `part` (reference order):
+ * out[n!][d][d], out[r] = rho_lambda(sigma_r).  Replaces SnIrrep.matrix_tensor /
+ * matrix_representations (irreps.py:122-148); used by slow_sn_ft / slow_sn_ift
+ * (fourier.py:82-108, 302-327).  n!*d*d elements: practical to n = 8.
+ */
+int snfft_dense_rep(const snfft_plan_t* plan, int part, void* out, void* stream);
+
+/* Number of kernel launches issued by this library since load (all threads). */
+int64_t snfft_launch_count(void);
+
+/* Test hook: shapes whose dimension fits kernel class `cls` (0..5) run in that
+ * class instead of the smallest fitting one; -1 restores the automatic choice.
+ * Affects plans created afterwards.  Lets small n exercise every kernel class. */
+void snfft_debug_force_class(int cls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNFFT_H */

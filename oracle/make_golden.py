@@ -1,0 +1,96 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, which does not exist
+on the GPU box):
+
+    python oracle/make_golden.py            # n = 2..7  (seconds)
+    python oracle/make_golden.py --n8       # adds n = 8 (about a minute, ~8 GB)
+
+What is recorded (every array comes from the reference's own code):
+  partitions_n{n}            generate_partitions(n)            tableau.py:103-123
+  n{n}_dims                  SnIrrep.dim per partition         irreps.py:40-44
+  n{n}_yor_{lam}_{j}         adj_transposition_matrix(j, j+1)  irreps.py:91-109   (n <= 6)
+  n{n}_coset_{i}             argwhere(sn_perms[:, i] == n-1)   fourier.py:77-80   (n <= 7)
+  n{n}_{dt}_f                seeded random input (B, n!)
+  n{n}_{dt}_ft_{lam}         sn_fft(f, n)[lam]                 fourier.py:281-288
+  n{n}_{dt}_ift              inverse of that ft: sn_ifft for n <= 5 (fourier.py:298-299);
+                             for n = 6, 7 the reference's dense inverse reached by
+                             BASE_CASE = n (fourier.py:134-165) because the recursive
+                             inverse raises there (fourier.py:202-214)
+"""
+import argparse
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, "/root/reference/src")
+import algebraist.fourier as RF                                     # noqa: E402
+from algebraist.irreps import SnIrrep                               # noqa: E402
+from algebraist.tableau import generate_partitions                  # noqa: E402
+from algebraist.utils import generate_all_permutations              # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def key(lam):
+    return "_".join(str(x) for x in lam)
+
+
+def tables():
+    out = {}
+    for n in range(1, 13):
+        parts = generate_partitions(n)
+        flat = np.zeros((len(parts), n), dtype=np.int64)
+        for r, p in enumerate(parts):
+            flat[r, :len(p)] = p
+        out[f"partitions_n{n}"] = flat
+    for n in range(2, 8):
+        perms = generate_all_permutations(n)
+        for i in range(n):
+            out[f"n{n}_coset_{i}"] = torch.argwhere(perms[:, i] == n - 1).squeeze().numpy()
+        dims = []
+        for lam in generate_partitions(n):
+            ir = SnIrrep(n, lam)
+            dims.append(ir.dim)
+            if n <= 6:
+                for j in range(n - 1):
+                    out[f"n{n}_yor_{key(lam)}_{j}"] = ir.adj_transposition_matrix(j, j + 1)
+        out[f"n{n}_dims"] = np.array(dims, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "tables.npz"), **out)
+
+
+def transforms(n, batch, dtypes, with_inverse=True):
+    out = {}
+    for dt_name, dt in dtypes:
+        torch.manual_seed(1000 + n)
+        f = torch.randn(batch, math.factorial(n), dtype=torch.float64).to(dt)
+        ft = RF.sn_fft(f, n)
+        out[f"n{n}_{dt_name}_f"] = f.numpy()
+        for lam, v in ft.items():
+            out[f"n{n}_{dt_name}_ft_{key(lam)}"] = v.numpy()
+        if with_inverse:
+            old = RF.BASE_CASE
+            if n > old:
+                RF.BASE_CASE = n          # dense inverse path, fourier.py:164-165
+            try:
+                out[f"n{n}_{dt_name}_ift"] = RF.sn_ifft(ft, n).numpy()
+            finally:
+                RF.BASE_CASE = old
+    np.savez_compressed(os.path.join(OUT, f"transform_n{n}.npz"), **out)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n8", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    both = [("f64", torch.float64), ("f32", torch.float32)]
+    if args.n8:
+        transforms(8, 1, both, with_inverse=False)
+    else:
+        tables()
+        for n in range(2, 8):
+            transforms(n, 3, both)

@@ -1,0 +1,132 @@
+import contextlib
+import ctypes
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_SO = os.path.join(EMU_DIR, "_build", "libsnfft_emu.so")
+CSRC = os.path.join(ROOT, "algebraist_b200", "csrc")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def key(lam):
+    return "_".join(str(x) for x in lam)
+
+
+@pytest.fixture(scope="session")
+def golden_tables():
+    return np.load(os.path.join(GOLDEN, "tables.npz"))
+
+
+def load_transform_golden(n):
+    return np.load(os.path.join(GOLDEN, f"transform_n{n}.npz"))
+
+
+def build_emu():
+    """g++ build of the CUDA sources against tests/emu/cuda_emu.h (tests only)."""
+    srcs = [os.path.join(CSRC, "snfft.cu"), os.path.join(CSRC, "plan.cpp")]
+    deps = srcs + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "plan.h"),
+                   os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "snfft.h")]
+    if os.path.exists(EMU_SO) and all(os.path.getmtime(d) <= os.path.getmtime(EMU_SO) for d in deps):
+        return EMU_SO
+    os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-x", "c++", "-DSNFFT_HOST_EMU", "-I" + EMU_DIR, "-shared", "-fPIC",
+           "-o", EMU_SO] + srcs
+    subprocess.run(cmd, check=True)
+    return EMU_SO
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """The C ABI compiled for the host (kernel logic check without a GPU)."""
+    from algebraist_b200 import _lib
+    return _lib.bind(ctypes.CDLL(build_emu()))
+
+
+class CAbi:
+    """Thin numpy front end over the C ABI, for a library whose 'device' pointers
+    are host pointers (the emulation build)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+
+    def plan(self, n, dtype):
+        h = ctypes.c_void_p()
+        rc = self.lib.snfft_plan_create(n, 0 if dtype == np.float32 else 1, 0, ctypes.byref(h))
+        assert rc == 0, self.lib.snfft_last_error()
+        return h
+
+    def forward(self, plan, f):
+        f = np.ascontiguousarray(f)
+        B = f.shape[0]
+        out = np.zeros(f.size, dtype=f.dtype)
+        ws = np.zeros(max(self.lib.snfft_workspace_bytes(plan, B), 8), dtype=np.uint8)
+        rc = self.lib.snfft_forward(plan, f.ctypes.data, B, out.ctypes.data, ws.ctypes.data, ws.nbytes, None)
+        assert rc == 0, self.lib.snfft_last_error()
+        return out
+
+    def inverse(self, plan, packed, B):
+        packed = np.ascontiguousarray(packed)
+        out = np.zeros((B, packed.size // B), dtype=packed.dtype)
+        ws = np.zeros(max(self.lib.snfft_workspace_bytes(plan, B), 8), dtype=np.uint8)
+        rc = self.lib.snfft_inverse(plan, packed.ctypes.data, B, out.ctypes.data, ws.ctypes.data, ws.nbytes, None)
+        assert rc == 0, self.lib.snfft_last_error()
+        return out
+
+
+def unpack(packed, n, B):
+    """packed C-ABI coefficient array -> dict lambda -> (B, d, d)."""
+    from oracle import sn_oracle as O
+    out, off = {}, 0
+    for lam in O.generate_partitions(n):
+        d = O.dim(lam)
+        out[lam] = packed[off * B:(off + d * d) * B].reshape(B, d, d)
+        off += d * d
+    assert off == math.factorial(n)
+    return out
+
+
+def pack(ft, n, B, dtype):
+    from oracle import sn_oracle as O
+    return np.concatenate([np.asarray(ft[lam], dtype=dtype).reshape(-1) for lam in O.generate_partitions(n)])
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@contextlib.contextmanager
+def package_on_emu(emu_lib):
+    """Route the Python package through the emulation library with CPU tensors.
+    Test-only: checks the wrappers' shape/dtype contract without a GPU."""
+    import torch
+    from algebraist_b200 import _lib, fourier, plan
+    saved = (_lib._lib, plan._DEVICE_TYPES, fourier._to_device, fourier._stream_ptr, fourier._device_ctx,
+             dict(plan._cache))
+    _lib._lib = emu_lib
+    plan._DEVICE_TYPES = ("cuda", "cpu")
+    plan._cache.clear()
+    fourier._to_device = lambda t: (t, t.device)
+    fourier._stream_ptr = lambda device: None
+    fourier._device_ctx = lambda device: contextlib.nullcontext()
+    try:
+        yield
+    finally:
+        plan._cache.clear()
+        (_lib._lib, plan._DEVICE_TYPES, fourier._to_device, fourier._stream_ptr, fourier._device_ctx, cache) = saved
+        plan._cache.update(cache)

@@ -1,0 +1,115 @@
+// Minimal CUDA-on-CPU shim used ONLY by the CPU test-suite (tests/): it lets
+// g++ compile algebraist_b200/csrc/snfft.cu unchanged so that the kernel logic
+// (indexing, tables, barriers) is checked against the oracle without a GPU.
+// It is not part of the product and the product never loads a library built
+// with it.  Threads of a block are ucontext fibers; __syncthreads() yields to
+// a round-robin scheduler, which gives exact barrier semantics on one OS thread.
+#pragma once
+#include <ucontext.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+inline dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(x)
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
+inline cudaError_t cudaGetLastError() { return 0; }
+inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+
+namespace emu {
+
+inline unsigned char* dyn_smem = nullptr;
+
+struct Sched {
+    ucontext_t main_ctx;
+    std::vector<ucontext_t> ctx;
+    std::vector<unsigned char> stacks;
+    std::vector<char> done;
+    const std::function<void()>* body = nullptr;
+    int cur = 0;
+    static constexpr size_t kStack = 256 * 1024;
+};
+inline Sched g;
+
+inline void trampoline() {
+    (*g.body)();
+    g.done[g.cur] = 1;
+    swapcontext(&g.ctx[g.cur], &g.main_ctx);
+}
+
+inline void yield_barrier() { swapcontext(&g.ctx[g.cur], &g.main_ctx); }
+
+inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+    const int nt = (int)(block.x * block.y * block.z);
+    std::vector<unsigned char> shared(smem + 64);
+    dyn_smem = shared.data();
+    if ((int)g.ctx.size() < nt) {
+        g.ctx.resize(nt);
+        g.stacks.resize((size_t)nt * Sched::kStack);
+    }
+    g.done.assign(nt, 0);
+    g.body = &body;
+    gridDim = grid;
+    blockDim = block;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                blockIdx = dim3(bx, by, bz);
+                for (int t = 0; t < nt; ++t) {
+                    getcontext(&g.ctx[t]);
+                    g.ctx[t].uc_stack.ss_sp = g.stacks.data() + (size_t)t * Sched::kStack;
+                    g.ctx[t].uc_stack.ss_size = Sched::kStack;
+                    g.ctx[t].uc_link = &g.main_ctx;
+                    makecontext(&g.ctx[t], trampoline, 0);
+                    g.done[t] = 0;
+                }
+                int alive = nt;
+                while (alive > 0) {
+                    alive = 0;
+                    for (int t = 0; t < nt; ++t) {
+                        if (g.done[t]) continue;
+                        g.cur = t;
+                        threadIdx = dim3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y,
+                                         (unsigned)t / (block.x * block.y));
+                        swapcontext(&g.main_ctx, &g.ctx[t]);
+                        if (!g.done[t]) ++alive;
+                    }
+                }
+            }
+    dyn_smem = nullptr;
+}
+
+}  // namespace emu
+
+inline void __syncthreads() { emu::yield_barrier(); }
+
+#define SNFFT_DYN_SMEM(name) unsigned char* name = emu::dyn_smem
+#define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) \
+    emu::launch(grid, block, smem, [&]() { kfn(__VA_ARGS__); })

@@ -1,0 +1,134 @@
+"""Kernel logic on the CPU: algebraist_b200/csrc/snfft.cu compiled by g++ against
+tests/emu/cuda_emu.h (blocks and __syncthreads emulated with fibers), called
+through the C ABI and compared with the oracle and the reference goldens.
+The GPU parity tests proper are in test_gpu_parity.py."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+from conftest import CAbi, key, load_transform_golden, pack, rel_err, unpack
+from oracle import sn_oracle as O
+
+DT = {"f32": np.float32, "f64": np.float64}
+TOL = {"f32": 1e-5, "f64": 1e-12}
+
+
+@pytest.mark.parametrize("n", range(2, 8))
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_forward_inverse_vs_reference_golden(emu, n, dt):
+    g = load_transform_golden(n)
+    f = g[f"n{n}_{dt}_f"]
+    B = f.shape[0]
+    abi = CAbi(emu)
+    plan = abi.plan(n, DT[dt])
+    try:
+        packed = abi.forward(plan, f)
+        ft = unpack(packed, n, B)
+        for lam in O.generate_partitions(n):
+            ref = g[f"n{n}_{dt}_ft_{key(lam)}"]
+            assert rel_err(ft[lam].reshape(ref.shape), ref) < TOL[dt], lam
+        inv = abi.inverse(plan, packed, B)
+        assert rel_err(inv, g[f"n{n}_{dt}_ift"]) < TOL[dt]
+        assert rel_err(inv, f) < TOL[dt]
+    finally:
+        emu.snfft_plan_destroy(plan)
+
+
+@pytest.mark.parametrize("cls", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_every_kernel_class(emu, cls, dt):
+    """Force all shapes of S_5 / S_6 through each kernel class (tile widths 32..2, row groups 1..256)."""
+    n, B = (6, 3) if cls <= 2 else (5, 5)
+    rng = np.random.default_rng(cls)
+    f = rng.standard_normal((B, math.factorial(n))).astype(DT[dt])
+    emu.snfft_debug_force_class(cls)
+    abi = CAbi(emu)
+    plan = abi.plan(n, DT[dt])
+    emu.snfft_debug_force_class(-1)
+    try:
+        packed = abi.forward(plan, f)
+        ref = O.sn_fft_packed(f.astype(np.float64), n)
+        ft = unpack(packed, n, B)
+        for lam in ref:
+            assert rel_err(ft[lam], ref[lam]) < TOL[dt], lam
+        assert rel_err(abi.inverse(plan, packed, B), f) < TOL[dt]
+    finally:
+        emu.snfft_plan_destroy(plan)
+
+
+@pytest.mark.parametrize("B", [1, 2, 7, 33, 70])
+def test_ragged_batches(emu, B):
+    n = 5
+    rng = np.random.default_rng(B)
+    f = rng.standard_normal((B, 120))
+    abi = CAbi(emu)
+    plan = abi.plan(n, np.float64)
+    try:
+        packed = abi.forward(plan, f)
+        ref = O.sn_fft_packed(f, n)
+        assert rel_err(packed, pack(ref, n, B, np.float64)) < 1e-12
+        assert rel_err(abi.inverse(plan, packed, B), f) < 1e-12
+    finally:
+        emu.snfft_plan_destroy(plan)
+
+
+def test_inverse_of_random_coefficients(emu):
+    """sn_ifft on arbitrary Fourier data (reference tests/test_fourier.py:153-159)."""
+    n, B = 6, 2
+    rng = np.random.default_rng(5)
+    ft = {lam: rng.standard_normal((B, O.dim(lam), O.dim(lam))) for lam in O.generate_partitions(n)}
+    abi = CAbi(emu)
+    plan = abi.plan(n, np.float64)
+    try:
+        inv = abi.inverse(plan, pack(ft, n, B, np.float64), B)
+        assert rel_err(inv, O.sn_ifft_packed(ft, n)) < 1e-12
+        assert rel_err(inv, O.slow_sn_ift_packed(ft, n)) < 1e-12
+    finally:
+        emu.snfft_plan_destroy(plan)
+
+
+@pytest.mark.parametrize("n", [3, 5, 7])
+def test_index_kernels_bit_exact(emu, n, golden_tables):
+    nf = math.factorial(n)
+    perms = O.all_permutations(n).astype(np.int8)
+    ranks = np.zeros(nf, dtype=np.int64)
+    assert emu.snfft_perm_rank(n, perms.ctypes.data, nf, ranks.ctypes.data, None) == 0
+    assert np.array_equal(ranks, np.arange(nf))
+    back = np.zeros((nf, n), dtype=np.int8)
+    assert emu.snfft_perm_unrank(n, ranks.ctypes.data, nf, back.ctypes.data, None) == 0
+    assert np.array_equal(back, perms)
+    for i in range(n):
+        idx = np.zeros(math.factorial(n - 1), dtype=np.int64)
+        assert emu.snfft_coset_index(n, i, idx.ctypes.data, None) == 0
+        assert np.array_equal(idx, golden_tables[f"n{n}_coset_{i}"].reshape(-1))
+    p1 = np.zeros(nf, dtype=np.int64)
+    assert emu.snfft_chain_index(n, p1.ctypes.data, None) == 0
+    g = O.gather_index(n)                       # instance -> rank, from restrict_to_coset recursion
+    assert np.array_equal(g[p1], np.arange(nf))
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+def test_dense_rep(emu, n):
+    abi = CAbi(emu)
+    plan = abi.plan(n, np.float64)
+    perms = O.all_permutations(n)
+    try:
+        for part, lam in enumerate(O.generate_partitions(n)):
+            d = O.dim(lam)
+            out = np.zeros((len(perms), d, d))
+            assert emu.snfft_dense_rep(plan, part, out.ctypes.data, None) == 0
+            ref = np.stack([O.rho(lam, s) for s in perms])
+            assert np.allclose(out, ref, atol=1e-13), lam
+    finally:
+        emu.snfft_plan_destroy(plan)
+
+
+def test_launch_counter(emu):
+    before = emu.snfft_launch_count()
+    abi = CAbi(emu)
+    plan = abi.plan(4, np.float32)
+    abi.forward(plan, np.zeros((1, 24), dtype=np.float32))
+    emu.snfft_plan_destroy(plan)
+    assert emu.snfft_launch_count() - before >= 4      # gather + levels 2..4
