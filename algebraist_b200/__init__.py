@@ -3,6 +3,7 @@
 Drop-in for the hot path of dashstander/algebraist (`sn_fft`, `sn_ifft`, plus
 the dense cross-checks `slow_sn_ft`, `slow_sn_ift`); mirrors
 `/root/reference/src/algebraist/__init__.py:16-19`."""
+from . import _lib
 from .fourier import sn_fft, sn_ifft, slow_sn_ft, slow_sn_ift
 
 __all__ = ["sn_fft", "sn_ifft", "slow_sn_ft", "slow_sn_ift"]

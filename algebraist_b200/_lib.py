@@ -17,6 +17,12 @@ c_vp = ctypes.c_void_p
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
 
+class ProfileRecord(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("level", ctypes.c_int32), ("kernel_class", ctypes.c_int32),
+                ("launches", ctypes.c_int32), ("elems_per_instance", ctypes.c_int64),
+                ("total_ms", ctypes.c_double)]
+
+
 # name -> (restype, argtypes); mirrors include/snfft.h one to one
 SIGNATURES = {
     "snfft_build_info": (ctypes.c_char_p, []),
@@ -44,6 +50,8 @@ SIGNATURES = {
     "snfft_coset_index": (c_int, [c_int, c_int, c_vp, c_vp]),
     "snfft_chain_index": (c_int, [c_int, c_vp, c_vp]),
     "snfft_dense_rep": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "snfft_profile_begin": (c_int, [c_vp]),
+    "snfft_profile_end": (c_int, [c_vp, ctypes.POINTER(ProfileRecord), c_int, ctypes.POINTER(c_int)]),
     "snfft_launch_count": (c_i64, []),
     "snfft_debug_force_class": (None, [c_int]),
 }

@@ -74,6 +74,7 @@ static int pick_class(int dtype, int d) {
 
 struct TaskRange {
     int cls, begin, count, max_dmu, max_dlam;
+    long long elems;      // coefficients this launch produces per instance (its share of k!)
 };
 
 struct DevLevel {
@@ -86,7 +87,15 @@ struct DevLevel {
 
 using namespace snfft;
 
+struct ProfEvent {
+    cudaEvent_t e0, e1;
+    int kind, k, cls;
+    long long elems;
+};
+
 struct snfft_plan {
+    bool prof_on = false;
+    std::vector<ProfEvent> prof;
     int n = 0, dtype = 0, device = 0;
     size_t esize = 4;
     HostPlan host;
@@ -170,8 +179,9 @@ static int build_level(snfft_plan* p, int k) {
         // big columns first: the long CTAs start early
         std::stable_sort(fby[c].begin(), fby[c].end(),
                          [](const FwdTask& x, const FwdTask& y) { return x.d_lam > y.d_lam; });
-        TaskRange r{c, (int)ftasks.size(), (int)fby[c].size(), 0, 0};
+        TaskRange r{c, (int)ftasks.size(), (int)fby[c].size(), 0, 0, 0};
         for (const FwdTask& t : fby[c]) {
+            r.elems += (long long)t.d_lam * t.d_mu;
             r.max_dmu = std::max(r.max_dmu, t.d_mu);
             r.max_dlam = std::max(r.max_dlam, t.d_lam);
             ftasks.push_back(t);
@@ -212,8 +222,9 @@ static int build_level(snfft_plan* p, int k) {
     std::vector<InvTask> itasks;
     for (int c = 0; c < kNumClasses; ++c) {
         if (iby[c].empty()) continue;
-        TaskRange r{c, (int)itasks.size(), (int)iby[c].size(), 0, 0};
+        TaskRange r{c, (int)itasks.size(), (int)iby[c].size(), 0, 0, 0};
         for (size_t q = 0; q < iby[c].size(); ++q) {
+            r.elems += (long long)k * iby[c][q].d_mu * iby[c][q].d_mu;
             r.max_dmu = std::max(r.max_dmu, iby[c][q].d_mu);
             r.max_dlam = std::max(r.max_dlam, iby_maxd[c][q]);
             itasks.push_back(iby[c][q]);
@@ -231,6 +242,32 @@ static int build_level(snfft_plan* p, int k) {
     if ((rc = upload(p, parents, &D.parents))) return rc;
     return SNFFT_OK;
 }
+
+// Optional per-launch CUDA-event timing (snfft_profile_begin / snfft_profile_end).
+struct ProfScope {
+    const snfft_plan* p;
+    cudaStream_t st;
+    ProfEvent ev;
+    bool on;
+    ProfScope(const snfft_plan* p_, cudaStream_t st_, int kind, int k, int cls, long long elems)
+        : p(p_), st(st_), on(p_->prof_on) {
+        if (!on) return;
+        ev.kind = kind;
+        ev.k = k;
+        ev.cls = cls;
+        ev.elems = elems;
+        if (cudaEventCreate(&ev.e0) != cudaSuccess || cudaEventCreate(&ev.e1) != cudaSuccess) {
+            on = false;
+            return;
+        }
+        cudaEventRecord(ev.e0, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(ev.e1, st);
+        const_cast<snfft_plan*>(p)->prof.push_back(ev);
+    }
+};
 
 static void tile_shape(int W, long long B, int* cw, int* ci) {
     int c = 1;
@@ -337,6 +374,7 @@ static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, 
     const bool fin = (k == p->n);
     for (const TaskRange& r : p->lev[k].franges) {
         int rc = SNFFT_ENOTSUP;
+        ProfScope prof(p, st, 0, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
             switch (r.cls) {
 #define SNFFT_CASE(id, dmax, W, G, RPT, NG) \
@@ -358,6 +396,7 @@ static int run_inv_level(const snfft_plan* p, int k, const void* in, void* out, 
     const bool first = (k == p->n);
     for (const TaskRange& r : p->lev[k].iranges) {
         int rc = SNFFT_ENOTSUP;
+        ProfScope prof(p, st, 1, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
             switch (r.cls) {
 #define SNFFT_CASE(id, dmax, W, G, RPT, NG) \
@@ -379,6 +418,7 @@ static int run_gather(const snfft_plan* p, const void* in, void* out, long long 
     ia.batch = B;
     dim3 grid((unsigned)((ia.nfact + GS_TR - 1) / GS_TR), (unsigned)((B + GS_TB - 1) / GS_TB), 1);
     dim3 block(GS_THREADS, 1, 1);
+    ProfScope prof(p, st, SCATTER ? 3 : 2, 1, -1, ia.nfact);
     auto kfn = gather_kernel<T, SCATTER>;
     SNFFT_LAUNCH(kfn, grid, block, gather_smem_bytes<T>(), st, (const T*)in, (T*)out, ia);
     g_launches.fetch_add(1);
@@ -677,6 +717,42 @@ int snfft_dense_rep(const snfft_plan_t* p, int part, void* out, void* stream) {
     }
     g_launches.fetch_add(1);
     SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
+}
+
+int snfft_profile_begin(snfft_plan_t* p) {
+    if (!p) return set_error(SNFFT_EINVAL, "plan is NULL");
+    for (ProfEvent& e : p->prof) {
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+    }
+    p->prof.clear();
+    p->prof_on = true;
+    return SNFFT_OK;
+}
+
+int snfft_profile_end(snfft_plan_t* p, snfft_profile_record_t* records, int max_records, int* n_records) {
+    if (!p || !n_records) return set_error(SNFFT_EINVAL, "NULL plan or n_records");
+    p->prof_on = false;
+    std::vector<snfft_profile_record_t> agg;
+    for (ProfEvent& e : p->prof) {
+        float ms = 0.f;
+        SNFFT_CUDA(cudaEventSynchronize(e.e1));
+        SNFFT_CUDA(cudaEventElapsedTime(&ms, e.e0, e.e1));
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+        bool found = false;
+        for (auto& r : agg)
+            if (r.kind == e.kind && r.level == e.k && r.kernel_class == e.cls) {
+                r.launches += 1;
+                r.total_ms += ms;
+                found = true;
+            }
+        if (!found) agg.push_back(snfft_profile_record_t{e.kind, e.k, e.cls, 1, (int64_t)e.elems, (double)ms});
+    }
+    p->prof.clear();
+    *n_records = (int)agg.size();
+    for (int i = 0; i < (int)agg.size() && i < max_records && records; ++i) records[i] = agg[i];
     return SNFFT_OK;
 }
 

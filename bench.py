@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the S_n FFT hot path (BASELINE.json: S_n FFT+IFFT transforms/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--n 10] [--batch 128] [--dtype f32|f64]
+
+A step is one forward + inverse transform of a batch of synthetic random
+functions (torch.randn, like the reference's tests/test_fourier.py:37-41).
+Default workload: S_10, batch 128 per GPU, fp32 (BASELINE.json configs[3]).
+With N > 1 (torchrun, one rank per GPU) the batch is sharded with no
+collective on the data path: every rank transforms its own 128 functions
+(weak scaling) and the value is the whole-job aggregate.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of
+the reference algorithm (oracle/) on the host cores instead.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sn_fft_ifft_pairs_per_s"
+UNIT = "transforms/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--n", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=128, help="functions per GPU")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"S{a.n} {a.dtype} FFT+IFFT, batch {a.batch} per GPU"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples),
+                "reasons": reasons}
+
+
+# --------------------------------------------------------------------------
+# CPU side: the oracle port of the reference algorithm
+# --------------------------------------------------------------------------
+def _oracle_pair(args):
+    n, dtype, seed = args
+    import numpy as np
+    from oracle import sn_oracle as O
+    f = np.random.default_rng(seed).standard_normal((1, math.factorial(n))).astype(dtype)
+    ft = O.sn_fft_packed(f, n)
+    inv = O.sn_ifft_packed(ft, n)
+    return float(abs(inv - f).max())
+
+
+def cpu_pairs_per_s(n, dtype, nfunc, workers):
+    """Forward+inverse of `nfunc` functions on `workers` host processes (oracle port)."""
+    import numpy as np
+    dt = np.float32 if dtype == "f32" else np.float64
+    jobs = [(n, dt, 1234 + i) for i in range(nfunc)]
+    t0 = time.perf_counter()
+    if workers <= 1:
+        for j in jobs:
+            _oracle_pair(j)
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            pool.map(_oracle_pair, jobs, chunksize=1)
+    return nfunc / (time.perf_counter() - t0)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    from oracle import sn_oracle as O
+    O.gather_index(a.n)                                  # tables warm (plan time, not step time)
+    for lam in O.generate_partitions(a.n):
+        for j in range(a.n - 1):
+            O.transposition_table(lam, j)
+    sample = workers                                      # one function per worker per step
+    times = []
+    for s in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        cpu_pairs_per_s(a.n, a.dtype, sample, workers)
+        if s >= a.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = sample * a.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * total / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(a), "n": a.n, "batch_per_gpu": a.batch,
+                   "note": "CPU oracle port of the reference algorithm (sparse YOR sweeps, numpy); the unmodified "
+                           "reference cannot run n >= 9 (SURVEY 0.3) and its recursive inverse raises for n > 5"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{sample} functions per step ({workers} processes x 1), forward+inverse"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# GPU side
+# --------------------------------------------------------------------------
+def run_native(a):
+    import torch
+    import torch.distributed as dist
+    from algebraist_b200 import _lib, sn_fft, sn_ifft
+    from algebraist_b200.plan import get_plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+    esize = 4 if a.dtype == "f32" else 8
+    n, B = a.n, a.batch
+    nf = math.factorial(n)
+    plan = get_plan(n, tdt, dev)
+    torch.manual_seed(1000 + rank)
+    f = torch.randn(B, nf, dtype=tdt, device=dev)
+    F = torch.empty(B * nf, dtype=tdt, device=dev)
+    f2 = torch.empty_like(f)
+    ws = plan.workspace(B)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        _lib.check(lib.snfft_forward(plan.handle, f.data_ptr(), B, F.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     stream.cuda_stream), "snfft_forward")
+        _lib.check(lib.snfft_inverse(plan.handle, F.data_ptr(), B, f2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     stream.cuda_stream), "snfft_inverse")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    err = ((f2 - f).double().norm() / f.double().norm()).item()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.snfft_launch_count()
+    _lib.check(lib.snfft_profile_begin(plan.handle), "profile_begin")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(a.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    recs = (_lib.ProfileRecord * 256)()
+    nrec = ctypes.c_int()
+    _lib.check(lib.snfft_profile_end(plan.handle, recs, 256, ctypes.byref(nrec)), "profile_end")
+    launches = lib.snfft_launch_count() - launches0
+    clocks = sampler.summary()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * a.steps / (ms / 1000.0)
+
+    # end to end through the public Python API with host buffers
+    f_host = torch.randn(B, nf, dtype=tdt).pin_memory()
+    out_host = torch.empty(B, nf, dtype=tdt).pin_memory()
+
+    def e2e_step():
+        x = f_host.to(dev, non_blocking=True)
+        y = sn_ifft(sn_fft(x, n), n)
+        out_host.copy_(y, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(a.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / e2e_s.item()
+    e2e_err = ((out_host - f_host).double().norm() / f_host.double().norm()).item()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kinds = {0: "fwd_level", 1: "inv_level", 2: "gather", 3: "scatter"}
+        kernels = []
+        for i in range(nrec.value):
+            r = recs[i]
+            ninst = B * (nf // math.factorial(r.level)) if r.kind < 2 else B
+            bytes_per_launch = 2 * r.elems_per_instance * ninst * esize
+            avg_ms = r.total_ms / r.launches
+            kernels.append({"kernel": f"{kinds[r.kind]}_k{r.level}_c{r.kernel_class}", "launches": r.launches,
+                            "avg_ms": avg_ms, "share": r.total_ms / ms,
+                            "alg_gbs": bytes_per_launch / (avg_ms * 1e-3) / 1e9})
+        kernels.sort(key=lambda k: -k["share"])
+        top = kernels[0]
+        alg_bytes_pair = 4 * nf * esize
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(a), "n": n, "batch_per_gpu": B, "parallelism": f"batch-shard x{world}",
+                       "l2_policy": f"inputs larger than L2 ({B * nf * esize / 1e6:.0f} MB per array per GPU)",
+                       "round_trip_rel_err": err},
+            "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": top["alg_gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": top["alg_gbs"] / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel_share_of_step": top["share"],
+                         "end_to_end_alg_gbs": value / world * alg_bytes_pair / 1e9,
+                         "end_to_end_frac": value / world * alg_bytes_pair / 1e9 / peak},
+            "kernels": kernels[:8],
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * nf * esize,
+                    "d2h_bytes_per_step": B * nf * esize, "steps": e2e_steps, "round_trip_rel_err": e2e_err,
+                    "path": "pinned host -> .to(cuda) -> sn_fft -> sn_ifft -> pinned host"},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            nfunc = 2 if n >= 10 else 8
+            v = cpu_pairs_per_s(n, a.dtype, nfunc, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{nfunc} functions of the same workload, forward+inverse, numpy oracle port"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)

@@ -149,6 +149,24 @@ int snfft_chain_index(int n, int64_t* p1_of_rank, void* stream);
  */
 int snfft_dense_rep(const snfft_plan_t* plan, int part, void* out, void* stream);
 
+/*
+ * Per-launch device timing with CUDA events on the launching stream.
+ * Between snfft_profile_begin and snfft_profile_end every kernel this plan
+ * launches is bracketed by an event pair; _end synchronises on them and returns
+ * one aggregated record per (kind, level, kernel class).
+ *   kind: 0 forward level, 1 inverse level, 2 input gather, 3 output scatter
+ *   elems_per_instance: coefficients the launch produces per function
+ *     (its share of k!; the launch reads as many), so its algorithmic traffic
+ *     is 2 * elems_per_instance * NINST_level * sizeof(dtype) bytes.
+ */
+typedef struct snfft_profile_record {
+    int32_t kind, level, kernel_class, launches;
+    int64_t elems_per_instance;
+    double total_ms;
+} snfft_profile_record_t;
+int snfft_profile_begin(snfft_plan_t* plan);
+int snfft_profile_end(snfft_plan_t* plan, snfft_profile_record_t* records, int max_records, int* n_records);
+
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t snfft_launch_count(void);
 

@@ -397,3 +397,89 @@ def slow_sn_ift_packed(ft: dict, n: int) -> np.ndarray:
         term = d * np.einsum('bij,gij->bg', np.asarray(ft[lam]).reshape(-1, d, d), mats)
         tot = term if tot is None else tot + term
     return tot / math.factorial(n)
+
+
+# ----------------------------------------------------------------------------
+# the same level steps with the inner loops in C (oracle/sn_oracle_c.c); the
+# tables still come from this file.  Used for the CPU baseline of bench.py and
+# for oracle checks at large n; pinned to the numpy path by tests/test_oracle_c.py.
+# ----------------------------------------------------------------------------
+_clib = None
+
+
+def c_library():
+    global _clib
+    if _clib is None:
+        import ctypes
+        from oracle import build_oracle
+        _clib = ctypes.CDLL(build_oracle.build())
+    return _clib
+
+
+@lru_cache(maxsize=None)
+def _c_tables(lam: tuple):
+    k = sum(lam)
+    p = np.ascontiguousarray(np.stack([transposition_table(lam, j)[0] for j in range(k - 1)]).astype(np.int32))
+    a = np.ascontiguousarray(np.stack([transposition_table(lam, j)[1] for j in range(k - 1)]))
+    b = np.ascontiguousarray(np.stack([transposition_table(lam, j)[2] for j in range(k - 1)]))
+    bo = np.array(block_offsets(lam), dtype=np.int32)
+    dm = np.array([dim(c) for c in children(lam)], dtype=np.int32)
+    return p, a, b, bo, dm
+
+
+def _c_level(k: int, data: dict, ninst: int, forward: bool) -> dict:
+    import ctypes
+    lib = c_library()
+    dt = next(iter(data.values())).dtype
+    suf = "f32" if dt == np.float32 else "f64"
+    fn = getattr(lib, ("snft_level_forward_" if forward else "snft_level_inverse_") + suf)
+    vp = ctypes.c_void_p
+    if forward:
+        out = {}
+    else:
+        out = {mu: np.zeros((dim(mu), dim(mu), k * ninst), dtype=dt) for mu in generate_partitions(k - 1)}
+    for lam in generate_partitions(k):
+        p, a, b, bo, dm = _c_tables(lam)
+        d = dim(lam)
+        ch = children(lam)
+        if forward:
+            ptrs = (vp * len(ch))(*[data[mu].ctypes.data for mu in ch])
+            res = np.empty((d, d, ninst), dtype=dt)
+            rc = fn(k, d, len(ch), vp(bo.ctypes.data), vp(dm.ctypes.data), ptrs, ctypes.c_int64(ninst),
+                    vp(p.ctypes.data), vp(a.ctypes.data), vp(b.ctypes.data), vp(res.ctypes.data))
+            out[lam] = res
+        else:
+            ptrs = (vp * len(ch))(*[out[mu].ctypes.data for mu in ch])
+            cur = np.ascontiguousarray(data[lam])
+            rc = fn(k, d, len(ch), vp(bo.ctypes.data), vp(dm.ctypes.data), ptrs, ctypes.c_int64(ninst),
+                    vp(p.ctypes.data), vp(a.ctypes.data), vp(b.ctypes.data), vp(cur.ctypes.data))
+        assert rc == 0
+    return out
+
+
+def sn_fft_packed_c(f: np.ndarray, n: int) -> dict:
+    """sn_fft_packed with C inner loops (same arithmetic order)."""
+    f = np.asarray(f)
+    assert f.ndim == 2 and f.shape[1] == math.factorial(n) and f.dtype in (np.float32, np.float64)
+    bsz = f.shape[0]
+    cur = {(1,): np.ascontiguousarray(f[:, gather_index(n)].T).reshape(1, 1, -1)}
+    ninst = f.shape[1] * bsz
+    for k in range(2, n + 1):
+        ninst //= k
+        cur = _c_level(k, cur, ninst, True)
+    return {lam: np.ascontiguousarray(np.moveaxis(v, 2, 0)) for lam, v in cur.items()}
+
+
+def sn_ifft_packed_c(ft: dict, n: int) -> np.ndarray:
+    parts = generate_partitions(n)
+    bsz = np.asarray(ft[parts[0]]).size
+    cur = {lam: np.ascontiguousarray(np.moveaxis(np.asarray(ft[lam]).reshape(bsz, dim(lam), dim(lam)), 0, 2))
+           for lam in parts}
+    ninst = bsz
+    for k in range(n, 1, -1):
+        cur = _c_level(k, cur, ninst, False)
+        ninst *= k
+    x1 = cur[(1,)].reshape(-1, bsz)
+    out = np.zeros((bsz, math.factorial(n)), dtype=x1.dtype)
+    out[:, gather_index(n)] = x1.T
+    return out

@@ -42,6 +42,12 @@ inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+typedef int cudaEvent_t;
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = 0; return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 
 namespace emu {
 
