@@ -54,6 +54,7 @@ SIGNATURES = {
     "snfft_profile_end": (c_int, [c_vp, ctypes.POINTER(ProfileRecord), c_int, ctypes.POINTER(c_int)]),
     "snfft_launch_count": (c_i64, []),
     "snfft_debug_force_class": (None, [c_int]),
+    "snfft_debug_disable_base": (None, [c_int]),
 }
 
 

@@ -19,15 +19,25 @@
 #pragma once
 #include <stdint.h>
 
+#include "base_gen.cuh"
+
 namespace snfft {
+
+// Sweep tables.  Every (lambda, child block b) pair of a level owns one blob of
+// 32-bit words in LevelArgs::tables:
+//   [0, k-1)        word offset (inside the blob) of the entries of rho_lambda(s_j), j = 0..k-2
+//   [k-1, 2(k-1))   npairs_j | nneg_j << 16
+//   entries of j    npairs_j rotations  t1 | t2 << 13 | code << 26, then nneg_j rows to negate
+// restricted to the rows the column can occupy before step j (see build_level).
+// `code` indexes LevelArgs::lut: a = lut[code] = 1/d, b = lut[LUT + code] = sqrt(1 - 1/d^2)
+// for the signed axial distance d (irreps.py:91-109):  x1' = a x1 + b x2 ; x2' = b x1 - a x2.
+constexpr int LUT = 24;
 
 struct FwdTask {          // one (lambda, child block b) pair of level k
     long long lam_off;    // coef_off(lambda)
     long long mu_off;     // coef_off(mu_b) in level k-1
-    int d_lam, d_mu, boff, lam;
-};
-struct OpRange {          // sweep rho_lambda(s_j): index lam * (k-1) + j
-    int pair_off, npairs, neg_off, nneg;
+    int d_lam, d_mu, boff;
+    int tab_off, tab_words, pad;
 };
 struct InvTask {          // one mu of level k-1
     long long mu_off;
@@ -35,7 +45,7 @@ struct InvTask {          // one mu of level k-1
 };
 struct InvParent {        // lambda covering mu
     long long lam_off;
-    int d_lam, boff, lam, pad;
+    int d_lam, boff, tab_off, tab_words;
     double scale;         // d_lambda / (k d_mu), fourier.py:191-199
 };
 
@@ -46,15 +56,22 @@ struct LevelArgs {
     const FwdTask* ftasks;
     const InvTask* itasks;
     const InvParent* parents;
-    const OpRange* ops;
-    const uint32_t* pair_rows;    // t1 | t2 << 16
-    const T* pair_coef;           // (a, b) per pair:  x1' = a x1 + b x2 ; x2' = b x1 - a x2
-    const uint32_t* neg_rows;     // rows with rho[t][t] = -1
+    const uint32_t* tables;
     int k;
-    int cw, ci;                   // column x instance tile of the packed-layout level (cw * ci == W)
-    int gstride;                  // elements of shared memory per column group
+    int cw, ci;                   // column x instance tile of the packed-layout level (cw * ci == TC)
+    int bstride;                  // elements of one work buffer (rows * TC)
+    int tab_smem_words;           // shared-memory words reserved for one task table
     long long ninst;              // NINST_k
     long long batch;              // B
+    T lut[2 * LUT];
+};
+
+// per-row tables of the full sweeps of level n (dense_rep_kernel only)
+template <typename T>
+struct RowTables {
+    const int* partner;           // [(lam_row_base + j * d) + t]
+    const T* diag;
+    const T* off;
 };
 
 struct IndexArgs {
@@ -112,44 +129,73 @@ __host__ __device__ inline long long chain_index(int n, long long r, const long 
 }
 
 // ---------------------------------------------------------------------------
-// sweep: work <- rho_lambda(s_j) work   (in place, rotations are disjoint)
+// sweep: work <- rho_lambda(s_j) work on the first `nact` work buffers
+// (in place; the rotations of one sweep touch disjoint rows).  Thread (rg, lane)
+// owns V adjacent columns and every G-th rotation of the list.
 // ---------------------------------------------------------------------------
-template <typename T, int W, int G>
-__device__ __forceinline__ void sweep(T* __restrict__ work, const LevelArgs<T>& a, int lam, int j,
-                                      int rg, int lane) {
-    const OpRange r = a.ops[lam * (a.k - 1) + j];
-    const uint32_t* __restrict__ rows = a.pair_rows + r.pair_off;
-    const T* __restrict__ coef = a.pair_coef + 2 * (size_t)r.pair_off;
-    int p = rg;
-    // two rotations per trip: independent loads first, then the math
-    for (; p + G < r.npairs; p += 2 * G) {
-        const uint32_t ra = rows[p], rb = rows[p + G];
-        const T a0 = coef[2 * p], b0 = coef[2 * p + 1];
-        const T a1 = coef[2 * (p + G)], b1 = coef[2 * (p + G) + 1];
-        T* pa1 = work + (ra & 0xffffu) * W + lane;
-        T* pa2 = work + (ra >> 16) * W + lane;
-        T* pb1 = work + (rb & 0xffffu) * W + lane;
-        T* pb2 = work + (rb >> 16) * W + lane;
-        const T x1 = *pa1, x2 = *pa2, y1 = *pb1, y2 = *pb2;
-        *pa1 = a0 * x1 + b0 * x2;
-        *pa2 = b0 * x1 - a0 * x2;
-        *pb1 = a1 * y1 + b1 * y2;
-        *pb2 = b1 * y1 - a1 * y2;
+template <typename T, int V>
+struct alignas(sizeof(T) * V) Pack {
+    T v[V];
+};
+
+template <typename T, int V, int TC, int G, int NBUF>
+__device__ __forceinline__ void sweep(T* __restrict__ work, int bstride, int nact, const uint32_t* __restrict__ tab,
+                                      const T* __restrict__ lut, int k, int j, int rg, int lane) {
+    using P = Pack<T, V>;
+    const uint32_t cnt = tab[k - 1 + j];
+    const int npairs = (int)(cnt & 0xffffu), nneg = (int)(cnt >> 16);
+    const uint32_t* __restrict__ ent = tab + tab[j];
+    T* __restrict__ base = work + lane * V;
+    for (int p = rg; p < npairs; p += G) {
+        const uint32_t e = ent[p];
+        const int o1 = (int)(e & 0x1fffu) * TC, o2 = (int)((e >> 13) & 0x1fffu) * TC;
+        const T ca = lut[e >> 26], cb = lut[LUT + (e >> 26)];
+        P x1[NBUF], x2[NBUF];
+#pragma unroll
+        for (int m = 0; m < NBUF; ++m)
+            if (m < nact) {
+                x1[m] = *reinterpret_cast<const P*>(base + m * bstride + o1);
+                x2[m] = *reinterpret_cast<const P*>(base + m * bstride + o2);
+            }
+#pragma unroll
+        for (int m = 0; m < NBUF; ++m)
+            if (m < nact) {
+                P y1, y2;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    y1.v[v] = ca * x1[m].v[v] + cb * x2[m].v[v];
+                    y2.v[v] = cb * x1[m].v[v] - ca * x2[m].v[v];
+                }
+                *reinterpret_cast<P*>(base + m * bstride + o1) = y1;
+                *reinterpret_cast<P*>(base + m * bstride + o2) = y2;
+            }
     }
-    for (; p < r.npairs; p += G) {
-        const uint32_t ra = rows[p];
-        const T a0 = coef[2 * p], b0 = coef[2 * p + 1];
-        T* pa1 = work + (ra & 0xffffu) * W + lane;
-        T* pa2 = work + (ra >> 16) * W + lane;
-        const T x1 = *pa1, x2 = *pa2;
-        *pa1 = a0 * x1 + b0 * x2;
-        *pa2 = b0 * x1 - a0 * x2;
+    for (int q = rg; q < nneg; q += G) {
+        const int o = (int)ent[npairs + q] * TC;
+#pragma unroll
+        for (int m = 0; m < NBUF; ++m)
+            if (m < nact) {
+                P x = *reinterpret_cast<const P*>(base + m * bstride + o);
+#pragma unroll
+                for (int v = 0; v < V; ++v) x.v[v] = -x.v[v];
+                *reinterpret_cast<P*>(base + m * bstride + o) = x;
+            }
     }
-    const uint32_t* __restrict__ neg = a.neg_rows + r.neg_off;
-    for (int q = rg; q < r.nneg; q += G) {
-        T* px = work + neg[q] * W + lane;
-        *px = -*px;
-    }
+}
+
+// Shared memory of a level kernel: [work buffers][lut][task table]
+template <typename T>
+__host__ __device__ inline size_t level_smem_bytes(int ng, int nbuf, int bstride, int tab_words) {
+    return ((size_t)ng * nbuf * bstride + 2 * LUT) * sizeof(T) + (size_t)tab_words * sizeof(uint32_t);
+}
+
+// Copy one task table into shared memory (STAGE) or use it in place.
+template <bool STAGE>
+__device__ __forceinline__ const uint32_t* stage_table(uint32_t* tab_s, const uint32_t* __restrict__ tables,
+                                                      int tab_off, int tab_words, int tid, int nthreads) {
+    if (!STAGE) return tables + tab_off;
+    for (int w = tid; w < tab_words; w += nthreads) tab_s[w] = tables[tab_off + w];
+    return tab_s;
 }
 
 template <int G>
@@ -157,188 +203,409 @@ __device__ __forceinline__ void group_sync() {
     if (G > 1) __syncthreads();
 }
 
+// Column tile bookkeeping shared by the forward and inverse kernels.
+// A tile is TC = W * V "slots"; a slot is one (column c, instance) pair of the
+// task's child block.  Threads have two roles:
+//   transfer role: slot fs = lt % TC, rows fr, fr + FR, ...   (global <-> shared, coalesced)
+//   sweep role   : V slots lane*V.., rows / rotations rg, rg + G, ...
+// Intermediate levels enumerate slots instance-fastest over the flattened
+// (c, inst) range; the packed-layout level uses a cw x ci tile and two slot
+// orders so that both its loads and its stores are contiguous.
+struct SlotMap {
+    long long c_ld, inst_ld, c_st, inst_st;   // (column, instance) of this thread's slot when loading / storing
+    int src_slot;                             // slot (load order) that holds the (c_st, inst_st) data
+    bool ok_ld, ok_st;
+};
+
+template <int TC, bool PACKED_IS_INPUT>
+__device__ __forceinline__ SlotMap make_slots(bool packed, long long chunk, int fs, int d_mu, long long ninst,
+                                              long long batch, int cw, int ci, long long* nchunks) {
+    SlotMap s;
+    if (packed) {
+        const long long ncx = (d_mu + cw - 1) / cw, nbx = (batch + ci - 1) / ci;
+        *nchunks = ncx * nbx;
+        const long long cx = chunk % ncx, bx = chunk / ncx;
+        // instance-fastest order: slot = c_rel * ci + i_rel ; column-fastest order: slot = i_rel * cw + c_rel
+        const long long c_if = cx * cw + fs / ci, i_if = bx * ci + fs % ci;
+        const long long c_cf = cx * cw + fs % cw, i_cf = bx * ci + fs / cw;
+        if (PACKED_IS_INPUT) {            // load column-fastest (packed input), store instance-fastest
+            s.c_ld = c_cf; s.inst_ld = i_cf; s.c_st = c_if; s.inst_st = i_if;
+            s.src_slot = (fs % ci) * cw + fs / ci;
+        } else {                          // load instance-fastest, store column-fastest (packed output)
+            s.c_ld = c_if; s.inst_ld = i_if; s.c_st = c_cf; s.inst_st = i_cf;
+            s.src_slot = (fs % cw) * ci + fs / cw;
+        }
+        s.ok_ld = chunk < *nchunks && s.c_ld < d_mu && s.inst_ld < batch;
+        s.ok_st = chunk < *nchunks && s.c_st < d_mu && s.inst_st < batch;
+    } else {
+        const long long qn = (long long)d_mu * ninst;
+        *nchunks = (qn + TC - 1) / TC;
+        const long long q = chunk * TC + fs;
+        s.c_ld = s.c_st = q / ninst;
+        s.inst_ld = s.inst_st = q % ninst;
+        s.src_slot = fs;
+        s.ok_ld = s.ok_st = q < qn;
+    }
+    return s;
+}
+
 // ---------------------------------------------------------------------------
 // forward level step S_{k-1} -> S_k      grid (chunks, tasks)
 // ---------------------------------------------------------------------------
-template <typename T, int W, int G, int RPT, int NG, bool FINAL>
-__global__ void __launch_bounds__(W* G* NG) fwd_level_kernel(const LevelArgs<T> a) {
+template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE, bool FINAL>
+__global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelArgs<T> a) {
     SNFFT_DYN_SMEM(smem_raw);
+    constexpr int TC = W * V, GT = W * G, FR = GT / TC;
     static_assert(G == 1 || NG == 1, "row groups need the whole CTA barrier");
+    static_assert(GT % TC == 0, "transfer role needs whole rows of threads");
+    using P = Pack<T, V>;
     const FwdTask tk = a.ftasks[blockIdx.y];
     const int tid = threadIdx.x;
-    const int grp = tid / (W * G), lt = tid % (W * G), rg = lt / W, lane = lt % W;
+    const int grp = tid / GT, lt = tid % GT, rg = lt / W, lane = lt % W;
+    const int fs = lt % TC, fr = lt / TC;
     const long long chunk = (long long)blockIdx.x * NG + grp;
     const int k = a.k;
     const long long ninst = a.ninst, ninst_prev = a.ninst * k;
 
-    long long c_in, inst_in, nchunks;
-    long long cx = 0, bx = 0;
-    if (FINAL) {
-        const long long ncx = (tk.d_mu + a.cw - 1) / a.cw, nbx = (a.batch + a.ci - 1) / a.ci;
-        nchunks = ncx * nbx;
-        cx = chunk % ncx;
-        bx = chunk / ncx;
-        c_in = cx * a.cw + lane / a.ci;          // load mapping: instance fastest
-        inst_in = bx * a.ci + lane % a.ci;
-    } else {
-        const long long qn = (long long)tk.d_mu * ninst;
-        nchunks = (qn + W - 1) / W;
-        const long long q = chunk * W + lane;
-        c_in = q / ninst;
-        inst_in = q % ninst;
-    }
+    long long nchunks;
+    const SlotMap sm = make_slots<TC, false>(FINAL, chunk, fs, tk.d_mu, ninst, a.batch, a.cw, a.ci, &nchunks);
     if ((long long)blockIdx.x * NG >= nchunks) return;          // whole CTA idle
-    const bool active = chunk < nchunks && c_in < tk.d_mu && inst_in < ninst;
 
-    T* __restrict__ work = reinterpret_cast<T*>(smem_raw) + (size_t)grp * a.gstride;
-    const T* __restrict__ src = a.in + (tk.mu_off + c_in) * ninst_prev + inst_in;
+    const int bstride = a.bstride;
+    T* __restrict__ work = reinterpret_cast<T*>(smem_raw) + (size_t)grp * NBUF * bstride;
+    T* __restrict__ lut = reinterpret_cast<T*>(smem_raw) + (size_t)NG * NBUF * bstride;
+    if (tid < 2 * LUT) lut[tid] = a.lut[tid];
+    const uint32_t* __restrict__ tab = stage_table<STAGE>(reinterpret_cast<uint32_t*>(lut + 2 * LUT), a.tables,
+                                                          tk.tab_off, tk.tab_words, tid, W * G * NG);
+    __syncthreads();
+    const T* __restrict__ src = a.in + (tk.mu_off + sm.c_ld) * ninst_prev + sm.inst_ld;
     const long long rstride = (long long)tk.d_mu * ninst_prev;
 
-    T acc[RPT];
+    P acc[RPT];
 #pragma unroll
-    for (int q = 0; q < RPT; ++q) acc[q] = T(0);
+    for (int q = 0; q < RPT; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[q].v[v] = T(0);
 
-    for (int i = 0; i < k; ++i) {
-        // work <- embed_b( F^(i)_mu[:, c] )
-        for (int t = rg; t < tk.d_lam; t += G) {
+    for (int i0 = 0; i0 < k; i0 += NBUF) {
+        const int nb = (k - i0 < NBUF) ? (k - i0) : NBUF;
+        // work[m] <- embed_b( F^(i0+m)_mu[:, c] )
+        for (int t = fr; t < tk.d_lam; t += FR) {
             const int rr = t - tk.boff;
-            T v = T(0);
-            if (active && rr >= 0 && rr < tk.d_mu) v = src[rr * rstride + i * ninst];
-            work[t * W + lane] = v;
+            const bool inblk = sm.ok_ld && rr >= 0 && rr < tk.d_mu;
+#pragma unroll
+            for (int m = 0; m < NBUF; ++m)
+                if (m < nb) work[m * bstride + t * TC + fs] = inblk ? src[rr * rstride + (i0 + m) * ninst] : T(0);
         }
         group_sync<G>();
-        for (int j = k - 2; j >= i; --j) {       // rho(s_i) ... rho(s_{k-2}) . work
-            sweep<T, W, G>(work, a, tk.lam, j, rg, lane);
+        for (int j = k - 2; j >= i0; --j) {       // rho(s_i) ... rho(s_{k-2}) . work
+            const int nact = (j - i0 + 1 < nb) ? (j - i0 + 1) : nb;
+            sweep<T, V, TC, G, NBUF>(work, bstride, nact, tab, lut, k, j, rg, lane);
             group_sync<G>();
         }
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int t = rg + q * G;
-            if (t < tk.d_lam) acc[q] += work[t * W + lane];
-        }
+        for (int m = 0; m < NBUF; ++m)
+            if (m < nb) {
+#pragma unroll
+                for (int q = 0; q < RPT; ++q) {
+                    const int t = rg + q * G;
+                    if (t < tk.d_lam) {
+                        const P x = *reinterpret_cast<const P*>(work + m * bstride + t * TC + lane * V);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[q].v[v] += x.v[v];
+                    }
+                }
+            }
         group_sync<G>();
     }
 
-    if (FINAL) {
-        // transpose the tile through shared memory so that stores run along columns
+    // results leave through shared memory so that the global stores are contiguous
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int t = rg + q * G;
-            if (t < tk.d_lam) work[t * W + lane] = acc[q];
-        }
-        __syncthreads();
-        const int c_rel = lane % a.cw, i_rel = lane / a.cw;
-        const long long c_out = cx * a.cw + c_rel, inst_out = bx * a.ci + i_rel;
-        const int slot = c_rel * a.ci + i_rel;
-        if (chunk < nchunks && c_out < tk.d_mu && inst_out < a.batch) {
-            T* __restrict__ dst = a.out + tk.lam_off * a.batch +
-                                  inst_out * ((long long)tk.d_lam * tk.d_lam) + tk.boff + c_out;
-            for (int t = rg; t < tk.d_lam; t += G) dst[(long long)t * tk.d_lam] = work[t * W + slot];
-        }
-    } else if (active) {
-        T* __restrict__ dst = a.out + (tk.lam_off + tk.boff + c_in) * ninst + inst_in;
-        const long long ostride = (long long)tk.d_lam * ninst;
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int t = rg + q * G;
-            if (t < tk.d_lam) dst[t * ostride] = acc[q];
+    for (int q = 0; q < RPT; ++q) {
+        const int t = rg + q * G;
+        if (t < tk.d_lam) *reinterpret_cast<P*>(work + t * TC + lane * V) = acc[q];
+    }
+    __syncthreads();
+    if (sm.ok_st) {
+        if (FINAL) {
+            T* __restrict__ dst = a.out + tk.lam_off * a.batch + sm.inst_st * ((long long)tk.d_lam * tk.d_lam) +
+                                  tk.boff + sm.c_st;
+            for (int t = fr; t < tk.d_lam; t += FR) dst[(long long)t * tk.d_lam] = work[t * TC + sm.src_slot];
+        } else {
+            T* __restrict__ dst = a.out + (tk.lam_off + tk.boff + sm.c_st) * ninst + sm.inst_st;
+            const long long ostride = (long long)tk.d_lam * ninst;
+            for (int t = fr; t < tk.d_lam; t += FR) dst[t * ostride] = work[t * TC + sm.src_slot];
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// inverse (adjoint) level step S_k -> S_{k-1}     grid (chunks, tasks, cosets)
+// inverse (adjoint) level step S_k -> S_{k-1}     grid (chunks * coset groups, tasks)
 //   G^(i)_mu[:, c] = sum_{lambda covers mu} d_lambda/(k d_mu) *
 //                    [ rho(s_{k-2}) ... rho(s_i) F_lambda[:, boff + c] ]_{rows of block mu}
+// The coset group index is the fastest grid dimension so that the CTAs that
+// re-read one column tile of F_lambda run together and hit in L2.
 // ---------------------------------------------------------------------------
-template <typename T, int W, int G, int RPT, int NG, bool FIRST>
-__global__ void __launch_bounds__(W* G* NG) inv_level_kernel(const LevelArgs<T> a) {
+template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE, bool FIRST>
+__global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelArgs<T> a) {
     SNFFT_DYN_SMEM(smem_raw);
+    constexpr int TC = W * V, GT = W * G, FR = GT / TC;
     static_assert(G == 1 || NG == 1, "row groups need the whole CTA barrier");
+    static_assert(GT % TC == 0, "transfer role needs whole rows of threads");
+    using P = Pack<T, V>;
     const InvTask tk = a.itasks[blockIdx.y];
-    const int i = blockIdx.z;
-    const int tid = threadIdx.x;
-    const int grp = tid / (W * G), lt = tid % (W * G), rg = lt / W, lane = lt % W;
-    const long long chunk = (long long)blockIdx.x * NG + grp;
     const int k = a.k;
+    const int ngroups = (k + NBUF - 1) / NBUF;
+    const int i0 = (int)(blockIdx.x % ngroups) * NBUF;
+    const int nb = (k - i0 < NBUF) ? (k - i0) : NBUF;
+    const int tid = threadIdx.x;
+    const int grp = tid / GT, lt = tid % GT, rg = lt / W, lane = lt % W;
+    const int fs = lt % TC, fr = lt / TC;
+    const long long cblock = blockIdx.x / ngroups;
+    const long long chunk = cblock * NG + grp;
     const long long ninst = a.ninst, ninst_prev = a.ninst * k;
 
-    long long c_in, inst_in, nchunks;
-    long long cx = 0, bx = 0;
-    if (FIRST) {
-        const long long ncx = (tk.d_mu + a.cw - 1) / a.cw, nbx = (a.batch + a.ci - 1) / a.ci;
-        nchunks = ncx * nbx;
-        cx = chunk % ncx;
-        bx = chunk / ncx;
-        c_in = cx * a.cw + lane % a.cw;          // load mapping: column fastest
-        inst_in = bx * a.ci + lane / a.cw;
-    } else {
-        const long long qn = (long long)tk.d_mu * ninst;
-        nchunks = (qn + W - 1) / W;
-        const long long q = chunk * W + lane;
-        c_in = q / ninst;
-        inst_in = q % ninst;
-    }
-    if ((long long)blockIdx.x * NG >= nchunks) return;
-    const bool active = chunk < nchunks && c_in < tk.d_mu && inst_in < ninst;
+    long long nchunks;
+    const SlotMap sm = make_slots<TC, true>(FIRST, chunk, fs, tk.d_mu, ninst, a.batch, a.cw, a.ci, &nchunks);
+    if (cblock * NG >= nchunks) return;
 
-    T* __restrict__ work = reinterpret_cast<T*>(smem_raw) + (size_t)grp * a.gstride;
+    const int bstride = a.bstride;
+    T* __restrict__ work = reinterpret_cast<T*>(smem_raw) + (size_t)grp * NBUF * bstride;
+    T* __restrict__ lut = reinterpret_cast<T*>(smem_raw) + (size_t)NG * NBUF * bstride;
+    if (tid < 2 * LUT) lut[tid] = a.lut[tid];
 
-    T acc[RPT];
+    P acc[NBUF][RPT];
 #pragma unroll
-    for (int q = 0; q < RPT; ++q) acc[q] = T(0);
+    for (int m = 0; m < NBUF; ++m)
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[m][q].v[v] = T(0);
 
     for (int p = 0; p < tk.npar; ++p) {
         const InvParent par = a.parents[tk.par_off + p];
         const T* __restrict__ src;
         long long rstride;
         if (FIRST) {
-            src = a.in + par.lam_off * a.batch + inst_in * ((long long)par.d_lam * par.d_lam) +
-                  par.boff + c_in;
+            src = a.in + par.lam_off * a.batch + sm.inst_ld * ((long long)par.d_lam * par.d_lam) + par.boff + sm.c_ld;
             rstride = par.d_lam;
         } else {
-            src = a.in + (par.lam_off + par.boff + c_in) * ninst + inst_in;
+            src = a.in + (par.lam_off + par.boff + sm.c_ld) * ninst + sm.inst_ld;
             rstride = (long long)par.d_lam * ninst;
         }
-        for (int t = rg; t < par.d_lam; t += G) work[t * W + lane] = active ? src[t * rstride] : T(0);
-        group_sync<G>();
-        for (int j = i; j <= k - 2; ++j) {       // rho(c_i)^T = rho(s_{k-2}) ... rho(s_i)
-            sweep<T, W, G>(work, a, par.lam, j, rg, lane);
+        const uint32_t* __restrict__ tab = stage_table<STAGE>(reinterpret_cast<uint32_t*>(lut + 2 * LUT), a.tables,
+                                                              par.tab_off, par.tab_words, tid, W * G * NG);
+        for (int t = fr; t < par.d_lam; t += FR) {
+            const T x = sm.ok_ld ? src[t * rstride] : T(0);
+#pragma unroll
+            for (int m = 0; m < NBUF; ++m)
+                if (m < nb) work[m * bstride + t * TC + fs] = x;
+        }
+        __syncthreads();
+        for (int j = i0; j <= k - 2; ++j) {      // rho(c_i)^T = rho(s_{k-2}) ... rho(s_i)
+            const int nact = (j - i0 + 1 < nb) ? (j - i0 + 1) : nb;
+            sweep<T, V, TC, G, NBUF>(work, bstride, nact, tab, lut, k, j, rg, lane);
             group_sync<G>();
         }
         const T scale = (T)par.scale;
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int t = rg + q * G;
-            if (t < tk.d_mu) acc[q] += scale * work[(par.boff + t) * W + lane];
-        }
-        group_sync<G>();
+        for (int m = 0; m < NBUF; ++m)
+            if (m < nb) {
+#pragma unroll
+                for (int q = 0; q < RPT; ++q) {
+                    const int t = rg + q * G;
+                    if (t < tk.d_mu) {
+                        const P x = *reinterpret_cast<const P*>(work + m * bstride + (par.boff + t) * TC + lane * V);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[m][q].v[v] += scale * x.v[v];
+                    }
+                }
+            }
+        __syncthreads();          // the next parent overwrites the work buffers and the staged table
     }
 
-    if (FIRST) {
+    // stage the results of all chains in shared memory, then store contiguously
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int t = rg + q * G;
-            if (t < tk.d_mu) work[t * W + lane] = acc[q];
+    for (int m = 0; m < NBUF; ++m)
+        if (m < nb) {
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                const int t = rg + q * G;
+                if (t < tk.d_mu) *reinterpret_cast<P*>(work + m * bstride + t * TC + lane * V) = acc[m][q];
+            }
         }
-        __syncthreads();
-        const int i_rel = lane % a.ci, c_rel = lane / a.ci;     // store mapping: instance fastest
-        const long long c_out = cx * a.cw + c_rel, inst_out = bx * a.ci + i_rel;
-        const int slot = i_rel * a.cw + c_rel;
-        if (chunk < nchunks && c_out < tk.d_mu && inst_out < a.batch) {
-            T* __restrict__ dst = a.out + (tk.mu_off + c_out) * ninst_prev + i * ninst + inst_out;
-            const long long ostride = (long long)tk.d_mu * ninst_prev;
-            for (int t = rg; t < tk.d_mu; t += G) dst[t * ostride] = work[t * W + slot];
-        }
-    } else if (active) {
-        T* __restrict__ dst = a.out + (tk.mu_off + c_in) * ninst_prev + i * ninst + inst_in;
+    __syncthreads();
+    if (sm.ok_st) {
         const long long ostride = (long long)tk.d_mu * ninst_prev;
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int t = rg + q * G;
-            if (t < tk.d_mu) dst[t * ostride] = acc[q];
-        }
+        for (int m = 0; m < NBUF; ++m)
+            if (m < nb) {
+                T* __restrict__ dst = a.out + (tk.mu_off + sm.c_st) * ninst_prev + (long long)(i0 + m) * ninst + sm.inst_st;
+                for (int t = fr; t < tk.d_mu; t += FR) dst[t * ostride] = work[m * bstride + t * TC + sm.src_slot];
+            }
     }
+}
+
+// ---------------------------------------------------------------------------
+// fused base kernels: levels 2..K0 (forward) / K0..2 (inverse) in shared memory.
+// A CTA owns TI consecutive level-K0 instances (one per lane); inside the tile a
+// level-k array is laid out like the global one with NINST replaced by P_k * TI,
+// P_k = K0!/k!:  element (coef e, chain p, lane) at (e * P_k + p) * TI + lane,
+// and the k cosets are the planes p_{k-1} = i * P_k + p.  Work items (task,
+// column c, chain p) are dealt to warps; every lane transforms its own instance,
+// so only level boundaries need a barrier.  One global read and one global write
+// replace K0-1 level passes.
+// ---------------------------------------------------------------------------
+template <typename T>
+struct BaseLevel {
+    const FwdTask* ftasks;
+    const InvTask* itasks;
+    const InvParent* parents;
+    const uint32_t* tables;
+    int nftasks, nitasks, tab_words, pad;
+    T lut[2 * LUT];
+};
+
+constexpr int BASE_MAXK = 6;
+
+template <typename T>
+struct BaseArgs {
+    const T* in;
+    T* out;
+    long long ninst;                  // NINST_{K0}
+    int k0, tab_smem_words;
+    long long fact[BASE_MAXK + 1];
+    BaseLevel<T> lev[BASE_MAXK + 1];  // lev[k], k = 2..k0
+};
+
+template <typename T, int TI, int NW, int DMAXB>
+__host__ __device__ inline size_t base_smem_bytes(int k0fact, int tab_words) {
+    return ((size_t)2 * k0fact * TI + (size_t)NW * DMAXB * TI + 2 * LUT) * sizeof(T) + (size_t)tab_words * sizeof(uint32_t);
+}
+
+template <typename T, int TI, int NW, int DMAXB, bool INVERSE>
+__global__ void __launch_bounds__(NW * 32) base_kernel(const BaseArgs<T> a) {
+    SNFFT_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int k0 = a.k0;
+    const int nf = (int)a.fact[k0];
+    T* bufA = reinterpret_cast<T*>(smem_raw);
+    T* bufB = bufA + (size_t)nf * TI;
+    T* scratch = bufB + (size_t)nf * TI + (size_t)warp * DMAXB * TI;
+    T* lut = bufB + (size_t)nf * TI + (size_t)NW * DMAXB * TI;
+    uint32_t* tab_s = reinterpret_cast<uint32_t*>(lut + 2 * LUT);
+    const long long i0 = (long long)blockIdx.x * TI;
+    const bool lane_ok = lane < TI;
+    const bool valid = lane_ok && i0 + lane < a.ninst;
+
+    // tile in: X_1 (forward) or X_{K0} (inverse); both are [K0!][NINST_{K0}] instance fastest
+    if (lane_ok)
+        for (int e = warp; e < nf; e += NW) bufA[e * TI + lane] = valid ? a.in[(long long)e * a.ninst + i0 + lane] : T(0);
+
+    T* cur = bufA;
+    T* nxt = bufB;
+    for (int step = 0; step < k0 - 1; ++step) {
+        const int k = INVERSE ? k0 - step : 2 + step;
+        const BaseLevel<T>& L = a.lev[k];
+        const int pk = (int)(a.fact[k0] / a.fact[k]);       // P_k
+        __syncthreads();                                    // previous level done, old table free
+        for (int w = tid; w < L.tab_words; w += NW * 32) tab_s[w] = L.tables[w];
+        if (tid < 2 * LUT) lut[tid] = L.lut[tid];
+        __syncthreads();
+        if (!INVERSE) {
+            for (int t = 0; t < L.nftasks; ++t) {
+                const FwdTask tk = L.ftasks[t];
+                const uint32_t* tab = tab_s + tk.tab_off;
+                const int nitems = tk.d_mu * pk;
+                for (int q = warp; q < nitems; q += NW) {
+                    if (!lane_ok) continue;
+                    const int c = q / pk, p = q % pk;
+                    T acc[DMAXB];
+#pragma unroll
+                    for (int r = 0; r < DMAXB; ++r) acc[r] = T(0);
+                    for (int i = 0; i < k; ++i) {
+                        for (int r = 0; r < tk.d_lam; ++r) scratch[r * TI + lane] = T(0);
+                        for (int r = 0; r < tk.d_mu; ++r)
+                            scratch[(tk.boff + r) * TI + lane] =
+                                cur[((int)(tk.mu_off + r * tk.d_mu + c) * (pk * k) + i * pk + p) * TI + lane];
+                        for (int j = k - 2; j >= i; --j) sweep<T, 1, TI, 1, 1>(scratch, 0, 1, tab, lut, k, j, 0, lane);
+#pragma unroll
+                        for (int r = 0; r < DMAXB; ++r)
+                            if (r < tk.d_lam) acc[r] += scratch[r * TI + lane];
+                    }
+#pragma unroll
+                    for (int r = 0; r < DMAXB; ++r)
+                        if (r < tk.d_lam)
+                            nxt[((int)(tk.lam_off + r * tk.d_lam + tk.boff + c) * pk + p) * TI + lane] = acc[r];
+                }
+            }
+        } else {
+            for (int t = 0; t < L.nitasks; ++t) {
+                const InvTask tk = L.itasks[t];
+                const int nitems = tk.d_mu * pk * k;
+                for (int q = warp; q < nitems; q += NW) {
+                    if (!lane_ok) continue;
+                    const int i = q % k, cp = q / k;
+                    const int c = cp / pk, p = cp % pk;
+                    T acc[DMAXB];
+#pragma unroll
+                    for (int r = 0; r < DMAXB; ++r) acc[r] = T(0);
+                    for (int pp = 0; pp < tk.npar; ++pp) {
+                        const InvParent par = L.parents[tk.par_off + pp];
+                        const uint32_t* tab = tab_s + par.tab_off;
+                        for (int r = 0; r < par.d_lam; ++r)
+                            scratch[r * TI + lane] =
+                                cur[((int)(par.lam_off + r * par.d_lam + par.boff + c) * pk + p) * TI + lane];
+                        for (int j = i; j <= k - 2; ++j) sweep<T, 1, TI, 1, 1>(scratch, 0, 1, tab, lut, k, j, 0, lane);
+                        const T scale = (T)par.scale;
+#pragma unroll
+                        for (int r = 0; r < DMAXB; ++r)
+                            if (r < tk.d_mu) acc[r] += scale * scratch[(par.boff + r) * TI + lane];
+                    }
+#pragma unroll
+                    for (int r = 0; r < DMAXB; ++r)
+                        if (r < tk.d_mu)
+                            nxt[((int)(tk.mu_off + r * tk.d_mu + c) * (pk * k) + i * pk + p) * TI + lane] = acc[r];
+                }
+            }
+        }
+        T* sw = cur;
+        cur = nxt;
+        nxt = sw;
+    }
+    __syncthreads();
+    if (valid)
+        for (int e = warp; e < nf; e += NW) a.out[(long long)e * a.ninst + i0 + lane] = cur[e * TI + lane];
+}
+
+// ---------------------------------------------------------------------------
+// generated register kernels for the lowest levels (base_gen.cuh, gen_base.py):
+// one instance per thread, lanes over consecutive instances so every global
+// access is a contiguous 128-byte row.
+//   s5_kernel : X_1 [120][NINST_5] -> X_5 [120][NINST_5]   (levels 2..5; inverse: 5..2)
+//   l6_kernel : X_5 [120*6][NINST_6] -> X_6 [720][NINST_6] (level 6; inverse: 6)
+// ---------------------------------------------------------------------------
+constexpr int GEN_THREADS = 128;
+
+template <typename T, bool INVERSE>
+__global__ void __launch_bounds__(GEN_THREADS) s5_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst5) {
+    const long long inst = (long long)blockIdx.x * GEN_THREADS + threadIdx.x;
+    if (inst >= ninst5) return;
+    T x[120], y[120];
+#pragma unroll
+    for (int p = 0; p < 120; ++p) x[p] = in[(size_t)p * ninst5 + inst];
+    if (INVERSE) s5_inverse<T>(x, y);
+    else s5_forward<T>(x, y);
+#pragma unroll
+    for (int e = 0; e < 120; ++e) out[(size_t)e * ninst5 + inst] = y[e];
+}
+
+template <typename T, bool INVERSE>
+__global__ void __launch_bounds__(GEN_THREADS) l6_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst6) {
+    const long long inst = (long long)blockIdx.x * GEN_THREADS + threadIdx.x;
+    if (inst >= ninst6) return;
+    if (INVERSE) l6_inverse<T>(in + inst, out + inst, (size_t)ninst6);
+    else l6_forward<T>(in + inst, out + inst, (size_t)ninst6);
 }
 
 // ---------------------------------------------------------------------------
@@ -446,20 +713,22 @@ __global__ void chain_index_kernel(long long* __restrict__ p1, const IndexArgs i
 // dense representation matrices rho_lambda(sigma) for every sigma in S_n
 // (SnIrrep.matrix_tensor, irreps.py:122-148), used by slow_sn_ft / slow_sn_ift.
 // sigma = c^(n)_{i_n} * ... * c^(2)_{i_2}  =>  rho(sigma) e_c is obtained by
-// applying the words s_i ... s_{k-2} for k = 2..n to the unit vector e_c.
-// One lane per (sigma, column); block of 32 lanes, column vectors in shared memory.
+// applying the words s_i ... s_{k-2} for k = 2..n to the unit vector e_c, each
+// s_j in gather form  y[t] = diag[t] x[t] + off[t] x[partner[t]]  (irreps.py:91-109).
+// One lane per (sigma, column); block of 32 lanes, two column buffers in shared memory.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(32) dense_rep_kernel(const LevelArgs<T> a, int lam, int d, T* __restrict__ out,
+__global__ void __launch_bounds__(32) dense_rep_kernel(const RowTables<T> tb, int d, T* __restrict__ out,
                                                          const IndexArgs ia) {
     SNFFT_DYN_SMEM(smem_raw);
-    T* work = reinterpret_cast<T*>(smem_raw);
+    T* x = reinterpret_cast<T*>(smem_raw);
+    T* y = x + d * 32;
     const int lane = threadIdx.x;
     const long long q = (long long)blockIdx.x * 32 + lane;
     const long long rank = q / d;
     const int c = (int)(q % d);
     if (rank >= ia.nfact) return;
-    for (int t = 0; t < d; ++t) work[t * 32 + lane] = (t == c) ? T(1) : T(0);
+    for (int t = 0; t < d; ++t) x[t * 32 + lane] = (t == c) ? T(1) : T(0);
     int sig[SNFFT_MAX_N];
     unrank_perm(ia.n, rank, ia.fact, sig);
     for (int k = 2; k <= ia.n; ++k) {
@@ -469,9 +738,17 @@ __global__ void __launch_bounds__(32) dense_rep_kernel(const LevelArgs<T> a, int
             if (sig[p] == v) break;
             i += sig[p] < v;
         }
-        for (int j = k - 2; j >= i; --j) sweep<T, 32, 1>(work, a, lam, j, 0, lane);
+        for (int j = k - 2; j >= i; --j) {
+            const int* __restrict__ pt = tb.partner + (size_t)j * d;
+            const T* __restrict__ dg = tb.diag + (size_t)j * d;
+            const T* __restrict__ of = tb.off + (size_t)j * d;
+            for (int t = 0; t < d; ++t) y[t * 32 + lane] = dg[t] * x[t * 32 + lane] + of[t] * x[pt[t] * 32 + lane];
+            T* tmp = x;
+            x = y;
+            y = tmp;
+        }
     }
-    for (int t = 0; t < d; ++t) out[(rank * d + t) * d + c] = work[t * 32 + lane];
+    for (int t = 0; t < d; ++t) out[(rank * d + t) * d + c] = x[t * 32 + lane];
 }
 
 }  // namespace snfft

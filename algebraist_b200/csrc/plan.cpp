@@ -163,6 +163,7 @@ void build_host_plan(int n, HostPlan& plan) {
             S.partner.assign(k - 1, std::vector<int32_t>(d));
             S.diag.assign(k - 1, std::vector<double>(d, 0.0));
             S.off.assign(k - 1, std::vector<double>(d, 0.0));
+            S.dist.assign(k - 1, std::vector<int8_t>(d, 0));
             // j <= k-3: block-diagonal stack of the children's tables
             for (int j = 0; j + 3 <= k; ++j) {
                 for (size_t b = 0; b < S.child.size(); ++b) {
@@ -171,6 +172,7 @@ void build_host_plan(int n, HostPlan& plan) {
                         S.partner[j][S.boff[b] + t] = C.partner[j][t] + S.boff[b];
                         S.diag[j][S.boff[b] + t] = C.diag[j][t];
                         S.off[j][S.boff[b] + t] = C.off[j][t];
+                        S.dist[j][S.boff[b] + t] = C.dist[j][t];
                     }
                 }
             }
@@ -181,6 +183,7 @@ void build_host_plan(int n, HostPlan& plan) {
             if (k == 2) {
                 // (2): same row, d = +1 ; (1,1): same column, d = -1
                 S.diag[j][0] = (S.rows.size() == 1) ? 1.0 : -1.0;
+                S.dist[j][0] = (S.rows.size() == 1) ? 1 : -1;
                 continue;
             }
             const HostLevel& Q = plan.levels[k - 2];
@@ -194,7 +197,10 @@ void build_host_plan(int n, HostPlan& plan) {
                     removed_box(M.rows, N.rows, ra, ca);
                     const int dist = (ra - rb) + (cb - ca);     // tableau.py:214-220
                     const int lo = S.boff[b] + M.boff[c];
-                    for (int t = 0; t < N.dim; ++t) S.diag[j][lo + t] = 1.0 / dist;
+                    for (int t = 0; t < N.dim; ++t) {
+                        S.diag[j][lo + t] = 1.0 / dist;
+                        S.dist[j][lo + t] = (int8_t)dist;
+                    }
                     if (std::abs(dist) > 1) {
                         // swapped tableau: k-1 in (ra,ca), k-2 in (rb,cb)
                         Part m2 = S.rows;

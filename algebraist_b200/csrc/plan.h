@@ -21,6 +21,7 @@ struct HostShape {
     //   rho[t][t] = diag[j][t], rho[t][partner[j][t]] = off[j][t]
     std::vector<std::vector<int32_t>> partner;
     std::vector<std::vector<double>> diag, off;
+    std::vector<std::vector<int8_t>> dist;   // signed axial distance, diag = 1 / dist (tableau.py:214-220)
 };
 
 struct HostLevel {

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -27,25 +28,32 @@
 namespace snfft {
 
 // ---------------------------------------------------------------------------
-// kernel classes: (id, dmax, W lanes, G row groups, RPT rows per thread, NG column groups per CTA)
-// A shape of dimension d runs in the first class with dmax >= d.
+// kernel classes: (id, dmax, V columns per thread, W lanes, G row groups, RPT rows per thread,
+//                  NG column groups per CTA, NBUF chains per pass, MINB CTAs per SM wanted,
+//                  STAGE the task table in shared memory)
+// A shape of dimension d runs in the first class with dmax >= d.  The column
+// tile is TC = V * W slots; shared memory = NG * NBUF * d * TC * sizeof(T) + table.
 // ---------------------------------------------------------------------------
-#define SNFFT_CLASSES_F32(X)                                                                   \
-    X(0, 16, 32, 1, 16, 8) X(1, 96, 32, 4, 24, 1) X(2, 256, 32, 8, 32, 1) X(3, 768, 32, 16, 48, 1) \
-    X(4, 2310, 16, 32, 73, 1) X(5, 7700, 4, 128, 61, 1)
-#define SNFFT_CLASSES_F64(X)                                                                   \
-    X(0, 16, 32, 1, 16, 8) X(1, 96, 32, 4, 24, 1) X(2, 256, 32, 8, 32, 1) X(3, 768, 32, 16, 48, 1) \
-    X(4, 2310, 8, 64, 37, 1) X(5, 7700, 2, 256, 31, 1)
+#define SNFFT_CLASSES_F32(X)                                                                            \
+    X(0, 16, 1, 32, 1, 16, 8, 1, 4, true) X(1, 96, 4, 8, 16, 6, 1, 2, 6, true)                          \
+    X(2, 256, 4, 8, 32, 8, 1, 2, 3, true) X(3, 768, 4, 4, 128, 6, 1, 2, 2, true)                        \
+    X(4, 2310, 4, 2, 512, 5, 1, 2, 1, true) X(5, 7700, 4, 1, 1024, 8, 1, 1, 1, false)
+#define SNFFT_CLASSES_F64(X)                                                                            \
+    X(0, 16, 1, 32, 1, 16, 8, 1, 4, true) X(1, 96, 2, 8, 16, 6, 1, 2, 6, true)                          \
+    X(2, 256, 2, 8, 32, 8, 1, 2, 3, true) X(3, 768, 2, 4, 128, 6, 1, 2, 2, true)                        \
+    X(4, 2310, 2, 2, 512, 5, 1, 2, 1, true) X(5, 7700, 2, 1, 1024, 8, 1, 1, 1, false)
 
 struct KClass {
-    int id, dmax, W, G, RPT, NG;
+    int id, dmax, V, W, G, RPT, NG, NBUF, MINB;
+    bool STAGE;
 };
-#define SNFFT_ROW(id, dmax, W, G, RPT, NG) {id, dmax, W, G, RPT, NG},
+#define SNFFT_ROW(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE) {id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE},
 static const KClass kClasses32[] = {SNFFT_CLASSES_F32(SNFFT_ROW)};
 static const KClass kClasses64[] = {SNFFT_CLASSES_F64(SNFFT_ROW)};
 static const int kNumClasses = 6;
 
 static std::atomic<int> g_force_class{-1};
+static std::atomic<int> g_no_base{0};
 static std::atomic<long long> g_launches{0};
 static thread_local std::string g_error;
 
@@ -73,13 +81,15 @@ static int pick_class(int dtype, int d) {
 }
 
 struct TaskRange {
-    int cls, begin, count, max_dmu, max_dlam;
+    int cls, begin, count, max_dmu, max_dlam, max_tab;
     long long elems;      // coefficients this launch produces per instance (its share of k!)
 };
 
 struct DevLevel {
-    void *ops = nullptr, *pair_rows = nullptr, *pair_coef = nullptr, *neg_rows = nullptr;
+    void* tables = nullptr;
     void *ftasks = nullptr, *itasks = nullptr, *parents = nullptr;
+    int nftasks = 0, nitasks = 0, tab_words = 0;
+    double lut_a[LUT], lut_b[LUT];
     std::vector<TaskRange> franges, iranges;
 };
 
@@ -102,6 +112,9 @@ struct snfft_plan {
     std::vector<DevLevel> lev;      // lev[k], k = 2..n
     std::vector<void*> allocs;      // every device allocation of the tables
     IndexArgs ia;
+    // per-row YOR tables of level n for snfft_dense_rep, uploaded on first use
+    void *rt_partner = nullptr, *rt_diag = nullptr, *rt_off = nullptr;
+    std::vector<long long> rt_base;     // per partition: offset of its [n-1][d] block
     // scratch of the *_host entry points
     void *h_in = nullptr, *h_out = nullptr, *h_ws = nullptr;
     size_t h_io_bytes = 0, h_ws_bytes = 0;
@@ -129,29 +142,66 @@ static int build_level(snfft_plan* p, int k) {
     DevLevel& D = p->lev[k];
     const int ns = (int)L.shapes.size();
 
-    std::vector<OpRange> ops((size_t)ns * (k - 1));
-    std::vector<uint32_t> pair_rows, neg_rows;
-    std::vector<T> pair_coef;
+    // Support-restricted sweeps.  A column of block b starts with support on the rows of
+    // block b; rho(s_{k-2}), rho(s_{k-3}), ... spread it.  The table of (lambda, b) lists, for
+    // every j, the rotations / sign flips of rho_lambda(s_j) that touch the support before
+    // step j (S_{j+1}); the inverse needs exactly the same lists (rows needed after step j).
+    // Coefficient codes: d in [2, k-1] -> d - 2 ; d in [-(k-1), -2] -> (k - 2) + (-d - 2).
+    for (int c = 0; c < LUT; ++c) D.lut_a[c] = D.lut_b[c] = 0.0;
+    for (int dd = 2; dd <= k - 1; ++dd) {
+        const double o = std::sqrt(1.0 - 1.0 / ((double)dd * dd));       // irreps.py:103-104
+        D.lut_a[dd - 2] = 1.0 / dd;
+        D.lut_b[dd - 2] = o;
+        D.lut_a[(k - 2) + dd - 2] = 1.0 / (-dd);
+        D.lut_b[(k - 2) + dd - 2] = o;
+    }
+    if (2 * (k - 2) > LUT) return set_error(SNFFT_ENOTSUP, "coefficient table too small for this n");
+    std::vector<uint32_t> tables;
+    std::vector<std::vector<int>> tab_off(ns), tab_words(ns);        // [lambda][b]
     for (int s = 0; s < ns; ++s) {
         const HostShape& S = L.shapes[s];
-        for (int j = 0; j <= k - 2; ++j) {
-            OpRange r;
-            r.pair_off = (int)pair_rows.size();
-            r.neg_off = (int)neg_rows.size();
-            for (int t = 0; t < S.dim; ++t) {
-                const int q = S.partner[j][t];
-                if (q > t) {
-                    pair_rows.push_back((uint32_t)t | ((uint32_t)q << 16));
-                    pair_coef.push_back((T)S.diag[j][t]);
-                    pair_coef.push_back((T)S.off[j][t]);
-                } else if (q == t) {
-                    if (S.diag[j][t] == -1.0) neg_rows.push_back((uint32_t)t);
-                    else if (S.diag[j][t] != 1.0) return set_error(SNFFT_EINVAL, "YOR table: unpaired row with |diag| != 1");
+        if (S.dim >= 8192) return set_error(SNFFT_ENOTSUP, "irrep dimension exceeds the 13-bit row field");
+        tab_off[s].resize(S.child.size());
+        tab_words[s].resize(S.child.size());
+        for (size_t b = 0; b < S.child.size(); ++b) {
+            const size_t base = tables.size();
+            tables.resize(base + 2 * (k - 1));
+            std::vector<char> sup(S.dim, 0);
+            const int dmu = P.shapes[S.child[b]].dim;
+            for (int t = 0; t < dmu; ++t) sup[S.boff[b] + t] = 1;
+            for (int j = k - 2; j >= 0; --j) {
+                const size_t start = tables.size();
+                std::vector<uint32_t> negs;
+                std::vector<int> grow;
+                for (int t = 0; t < S.dim; ++t) {
+                    const int q = S.partner[j][t];
+                    if (q > t) {
+                        if (!sup[t] && !sup[q]) continue;
+                        const int dd = S.dist[j][t];
+                        const int code = dd > 0 ? dd - 2 : (k - 2) + (-dd - 2);
+                        if (dd == 0 || dd == 1 || dd == -1 || code < 0 || code >= LUT ||
+                            D.lut_a[code] != S.diag[j][t] || D.lut_b[code] != S.off[j][t])
+                            return set_error(SNFFT_EINVAL, "YOR table: inconsistent axial distance");
+                        tables.push_back((uint32_t)t | ((uint32_t)q << 13) | ((uint32_t)code << 26));
+                        grow.push_back(t);
+                        grow.push_back(q);
+                    } else if (q == t) {
+                        if (S.diag[j][t] == -1.0) {
+                            if (sup[t]) negs.push_back((uint32_t)t);
+                        } else if (S.diag[j][t] != 1.0) {
+                            return set_error(SNFFT_EINVAL, "YOR table: unpaired row with |diag| != 1");
+                        }
+                    }
                 }
+                const size_t npairs = tables.size() - start;
+                if (npairs > 0xffff || negs.size() > 0xffff) return set_error(SNFFT_ENOTSUP, "sweep list too long");
+                tables.insert(tables.end(), negs.begin(), negs.end());
+                for (int t : grow) sup[t] = 1;
+                tables[base + j] = (uint32_t)(start - base);
+                tables[base + (k - 1) + j] = (uint32_t)npairs | ((uint32_t)negs.size() << 16);
             }
-            r.npairs = (int)pair_rows.size() - r.pair_off;
-            r.nneg = (int)neg_rows.size() - r.neg_off;
-            ops[(size_t)s * (k - 1) + j] = r;
+            tab_off[s][b] = (int)base;
+            tab_words[s][b] = (int)(tables.size() - base);
         }
     }
 
@@ -169,7 +219,9 @@ static int build_level(snfft_plan* p, int k) {
             t.d_lam = S.dim;
             t.d_mu = M.dim;
             t.boff = S.boff[b];
-            t.lam = s;
+            t.tab_off = tab_off[s][b];
+            t.tab_words = tab_words[s][b];
+            t.pad = 0;
             fby[cls].push_back(t);
         }
     }
@@ -179,9 +231,10 @@ static int build_level(snfft_plan* p, int k) {
         // big columns first: the long CTAs start early
         std::stable_sort(fby[c].begin(), fby[c].end(),
                          [](const FwdTask& x, const FwdTask& y) { return x.d_lam > y.d_lam; });
-        TaskRange r{c, (int)ftasks.size(), (int)fby[c].size(), 0, 0, 0};
+        TaskRange r{c, (int)ftasks.size(), (int)fby[c].size(), 0, 0, 0, 0};
         for (const FwdTask& t : fby[c]) {
             r.elems += (long long)t.d_lam * t.d_mu;
+            r.max_tab = std::max(r.max_tab, t.tab_words);
             r.max_dmu = std::max(r.max_dmu, t.d_mu);
             r.max_dlam = std::max(r.max_dlam, t.d_lam);
             ftasks.push_back(t);
@@ -191,7 +244,7 @@ static int build_level(snfft_plan* p, int k) {
 
     // inverse tasks: one per mu of level k-1, class by the largest covering lambda
     std::vector<std::vector<InvTask>> iby(kNumClasses);
-    std::vector<std::vector<int>> iby_maxd(kNumClasses);
+    std::vector<std::vector<int>> iby_maxd(kNumClasses), iby_maxtab(kNumClasses);
     std::vector<InvParent> parents;
     for (size_t m = 0; m < P.shapes.size(); ++m) {
         const HostShape& M = P.shapes[m];
@@ -201,15 +254,16 @@ static int build_level(snfft_plan* p, int k) {
         t.par_off = (int)parents.size();
         t.npar = (int)M.parent.size();
         t.pad = 0;
-        int maxd = 0;
+        int maxd = 0, maxtab = 0;
         for (size_t q = 0; q < M.parent.size(); ++q) {
             const HostShape& S = L.shapes[M.parent[q]];
             InvParent ip;
             ip.lam_off = S.coef_off;
             ip.d_lam = S.dim;
             ip.boff = S.boff[M.parent_block[q]];
-            ip.lam = M.parent[q];
-            ip.pad = 0;
+            ip.tab_off = tab_off[M.parent[q]][M.parent_block[q]];
+            ip.tab_words = tab_words[M.parent[q]][M.parent_block[q]];
+            maxtab = std::max(maxtab, ip.tab_words);
             ip.scale = (double)S.dim / ((double)k * (double)M.dim);
             parents.push_back(ip);
             maxd = std::max(maxd, S.dim);
@@ -218,12 +272,14 @@ static int build_level(snfft_plan* p, int k) {
         if (cls < 0) return set_error(SNFFT_ENOTSUP, "irrep dimension exceeds the largest kernel class");
         iby[cls].push_back(t);
         iby_maxd[cls].push_back(maxd);
+        iby_maxtab[cls].push_back(maxtab);
     }
     std::vector<InvTask> itasks;
     for (int c = 0; c < kNumClasses; ++c) {
         if (iby[c].empty()) continue;
-        TaskRange r{c, (int)itasks.size(), (int)iby[c].size(), 0, 0, 0};
+        TaskRange r{c, (int)itasks.size(), (int)iby[c].size(), 0, 0, 0, 0};
         for (size_t q = 0; q < iby[c].size(); ++q) {
+            r.max_tab = std::max(r.max_tab, iby_maxtab[c][q]);
             r.elems += (long long)k * iby[c][q].d_mu * iby[c][q].d_mu;
             r.max_dmu = std::max(r.max_dmu, iby[c][q].d_mu);
             r.max_dlam = std::max(r.max_dlam, iby_maxd[c][q]);
@@ -232,11 +288,11 @@ static int build_level(snfft_plan* p, int k) {
         D.iranges.push_back(r);
     }
 
+    D.nftasks = (int)ftasks.size();
+    D.nitasks = (int)itasks.size();
+    D.tab_words = (int)tables.size();
     int rc;
-    if ((rc = upload(p, ops, &D.ops))) return rc;
-    if ((rc = upload(p, pair_rows, &D.pair_rows))) return rc;
-    if ((rc = upload(p, pair_coef, &D.pair_coef))) return rc;
-    if ((rc = upload(p, neg_rows, &D.neg_rows))) return rc;
+    if ((rc = upload(p, tables, &D.tables))) return rc;
     if ((rc = upload(p, ftasks, &D.ftasks))) return rc;
     if ((rc = upload(p, itasks, &D.itasks))) return rc;
     if ((rc = upload(p, parents, &D.parents))) return rc;
@@ -269,11 +325,12 @@ struct ProfScope {
     }
 };
 
-static void tile_shape(int W, long long B, int* cw, int* ci) {
+// cw x ci tile (columns x instances) of the packed-layout level, cw * ci == TC
+static void tile_shape(int TC, long long B, int* cw, int* ci) {
     int c = 1;
-    while (c * 2 <= std::min(4, W) && c * 2 <= B) c *= 2;
+    while (c * 2 <= std::min(4, TC) && c * 2 <= B) c *= 2;
     *ci = c;
-    *cw = W / c;
+    *cw = TC / c;
 }
 
 template <typename KF>
@@ -288,28 +345,30 @@ static int set_smem(KF kfn, size_t bytes) {
     return SNFFT_OK;
 }
 
-template <typename T, int W, int G, int RPT, int NG>
+template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE>
 static int launch_fwd_range(const TaskRange& r, bool final_level, LevelArgs<T> a, cudaStream_t st) {
+    constexpr int TC = V * W;
     long long chunks;
     if (final_level) {
-        tile_shape(W, a.batch, &a.cw, &a.ci);
+        tile_shape(TC, a.batch, &a.cw, &a.ci);
         chunks = ((r.max_dmu + a.cw - 1) / a.cw) * ((a.batch + a.ci - 1) / a.ci);
     } else {
-        a.cw = W;
+        a.cw = TC;
         a.ci = 1;
-        chunks = ((long long)r.max_dmu * a.ninst + W - 1) / W;
+        chunks = ((long long)r.max_dmu * a.ninst + TC - 1) / TC;
     }
-    a.gstride = r.max_dlam * W;
+    a.bstride = r.max_dlam * TC;
     a.ftasks += r.begin;
-    const size_t smem = (size_t)NG * a.gstride * sizeof(T);
+    a.tab_smem_words = STAGE ? r.max_tab : 0;
+    const size_t smem = level_smem_bytes<T>(NG, NBUF, a.bstride, a.tab_smem_words);
     dim3 grid((unsigned)((chunks + NG - 1) / NG), (unsigned)r.count, 1), block(W * G * NG, 1, 1);
     int rc;
     if (final_level) {
-        auto kfn = fwd_level_kernel<T, W, G, RPT, NG, true>;
+        auto kfn = fwd_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, true>;
         if ((rc = set_smem(kfn, smem))) return rc;
         SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
     } else {
-        auto kfn = fwd_level_kernel<T, W, G, RPT, NG, false>;
+        auto kfn = fwd_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, false>;
         if ((rc = set_smem(kfn, smem))) return rc;
         SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
     }
@@ -318,28 +377,31 @@ static int launch_fwd_range(const TaskRange& r, bool final_level, LevelArgs<T> a
     return SNFFT_OK;
 }
 
-template <typename T, int W, int G, int RPT, int NG>
+template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE>
 static int launch_inv_range(const TaskRange& r, bool first_level, LevelArgs<T> a, cudaStream_t st) {
+    constexpr int TC = V * W;
     long long chunks;
     if (first_level) {
-        tile_shape(W, a.batch, &a.cw, &a.ci);
+        tile_shape(TC, a.batch, &a.cw, &a.ci);
         chunks = ((r.max_dmu + a.cw - 1) / a.cw) * ((a.batch + a.ci - 1) / a.ci);
     } else {
-        a.cw = W;
+        a.cw = TC;
         a.ci = 1;
-        chunks = ((long long)r.max_dmu * a.ninst + W - 1) / W;
+        chunks = ((long long)r.max_dmu * a.ninst + TC - 1) / TC;
     }
-    a.gstride = r.max_dlam * W;
+    a.bstride = r.max_dlam * TC;
     a.itasks += r.begin;
-    const size_t smem = (size_t)NG * a.gstride * sizeof(T);
-    dim3 grid((unsigned)((chunks + NG - 1) / NG), (unsigned)r.count, (unsigned)a.k), block(W * G * NG, 1, 1);
+    a.tab_smem_words = STAGE ? r.max_tab : 0;
+    const size_t smem = level_smem_bytes<T>(NG, NBUF, a.bstride, a.tab_smem_words);
+    const long long ngroups = (a.k + NBUF - 1) / NBUF;      // coset groups, fastest grid dimension
+    dim3 grid((unsigned)(((chunks + NG - 1) / NG) * ngroups), (unsigned)r.count, 1), block(W * G * NG, 1, 1);
     int rc;
     if (first_level) {
-        auto kfn = inv_level_kernel<T, W, G, RPT, NG, true>;
+        auto kfn = inv_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, true>;
         if ((rc = set_smem(kfn, smem))) return rc;
         SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
     } else {
-        auto kfn = inv_level_kernel<T, W, G, RPT, NG, false>;
+        auto kfn = inv_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, false>;
         if ((rc = set_smem(kfn, smem))) return rc;
         SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
     }
@@ -357,12 +419,13 @@ static LevelArgs<T> level_args(const snfft_plan* p, int k, const void* in, void*
     a.ftasks = (const FwdTask*)D.ftasks;
     a.itasks = (const InvTask*)D.itasks;
     a.parents = (const InvParent*)D.parents;
-    a.ops = (const OpRange*)D.ops;
-    a.pair_rows = (const uint32_t*)D.pair_rows;
-    a.pair_coef = (const T*)D.pair_coef;
-    a.neg_rows = (const uint32_t*)D.neg_rows;
+    a.tables = (const uint32_t*)D.tables;
+    for (int c = 0; c < LUT; ++c) {
+        a.lut[c] = (T)D.lut_a[c];
+        a.lut[LUT + c] = (T)D.lut_b[c];
+    }
     a.k = k;
-    a.cw = a.ci = a.gstride = 0;
+    a.cw = a.ci = a.bstride = a.tab_smem_words = 0;
     a.ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
     a.batch = B;
     return a;
@@ -377,8 +440,8 @@ static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, 
         ProfScope prof(p, st, 0, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
             switch (r.cls) {
-#define SNFFT_CASE(id, dmax, W, G, RPT, NG) \
-    case id: rc = launch_fwd_range<T, W, G, RPT, NG>(r, fin, a, st); break;
+#define SNFFT_CASE(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE) \
+    case id: rc = launch_fwd_range<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>(r, fin, a, st); break;
                 SNFFT_CLASSES_F32(SNFFT_CASE)
             }
         } else {
@@ -399,8 +462,8 @@ static int run_inv_level(const snfft_plan* p, int k, const void* in, void* out, 
         ProfScope prof(p, st, 1, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
             switch (r.cls) {
-#define SNFFT_CASE(id, dmax, W, G, RPT, NG) \
-    case id: rc = launch_inv_range<T, W, G, RPT, NG>(r, first, a, st); break;
+#define SNFFT_CASE(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE) \
+    case id: rc = launch_inv_range<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>(r, first, a, st); break;
                 SNFFT_CLASSES_F32(SNFFT_CASE)
             }
         } else {
@@ -426,6 +489,74 @@ static int run_gather(const snfft_plan* p, const void* in, void* out, long long 
     return SNFFT_OK;
 }
 
+// Fused levels 2..K0 (forward) or K0..2 (inverse) on level-K0 instance tiles.
+static const int kBaseK0 = 6;
+
+template <typename T, bool INVERSE>
+static int run_base(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
+    constexpr int TI = sizeof(T) == 4 ? 32 : 16, NW = 16, DMAXB = 16;
+    BaseArgs<T> a;
+    a.in = (const T*)in;
+    a.out = (T*)out;
+    a.k0 = kBaseK0;
+    a.ninst = B * (p->host.factorial[p->n] / p->host.factorial[kBaseK0]);
+    a.tab_smem_words = 0;
+    for (int k = 0; k <= BASE_MAXK; ++k) a.fact[k] = p->host.factorial[k];
+    for (int k = 2; k <= kBaseK0; ++k) {
+        const DevLevel& D = p->lev[k];
+        if (p->host.levels[k].max_dim > DMAXB) return set_error(SNFFT_ENOTSUP, "base kernel: irrep too large");
+        BaseLevel<T>& L = a.lev[k];
+        L.ftasks = (const FwdTask*)D.ftasks;
+        L.itasks = (const InvTask*)D.itasks;
+        L.parents = (const InvParent*)D.parents;
+        L.tables = (const uint32_t*)D.tables;
+        L.nftasks = D.nftasks;
+        L.nitasks = D.nitasks;
+        L.tab_words = D.tab_words;
+        L.pad = 0;
+        for (int c = 0; c < LUT; ++c) {
+            L.lut[c] = (T)D.lut_a[c];
+            L.lut[LUT + c] = (T)D.lut_b[c];
+        }
+        a.tab_smem_words = std::max(a.tab_smem_words, D.tab_words);
+    }
+    const size_t smem = base_smem_bytes<T, TI, NW, DMAXB>((int)p->host.factorial[kBaseK0], a.tab_smem_words);
+    dim3 grid((unsigned)((a.ninst + TI - 1) / TI), 1, 1), block(NW * 32, 1, 1);
+    ProfScope prof(p, st, INVERSE ? 5 : 4, kBaseK0, -1, p->host.factorial[kBaseK0]);
+    auto kfn = base_kernel<T, TI, NW, DMAXB, INVERSE>;
+    int rc;
+    if ((rc = set_smem(kfn, smem))) return rc;
+    SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
+    g_launches.fetch_add(1);
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
+}
+
+// Generated register kernels: levels 2..5 of every S_5 instance, and level 6.
+template <typename T, bool INVERSE>
+static int run_s5(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
+    const long long ninst = B * (p->host.factorial[p->n] / 120);
+    dim3 grid((unsigned)((ninst + GEN_THREADS - 1) / GEN_THREADS), 1, 1), block(GEN_THREADS, 1, 1);
+    ProfScope prof(p, st, INVERSE ? 5 : 4, 5, -1, 120);
+    auto kfn = s5_kernel<T, INVERSE>;
+    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)in, (T*)out, ninst);
+    g_launches.fetch_add(1);
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
+}
+
+template <typename T, bool INVERSE>
+static int run_l6(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
+    const long long ninst = B * (p->host.factorial[p->n] / 720);
+    dim3 grid((unsigned)((ninst + GEN_THREADS - 1) / GEN_THREADS), 1, 1), block(GEN_THREADS, 1, 1);
+    ProfScope prof(p, st, INVERSE ? 5 : 4, 6, -1, 720);
+    auto kfn = l6_kernel<T, INVERSE>;
+    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)in, (T*)out, ninst);
+    g_launches.fetch_add(1);
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
+}
+
 template <typename T>
 static int forward_impl(const snfft_plan* p, const void* f, long long B, void* F, void* ws, cudaStream_t st) {
     const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
@@ -433,7 +564,23 @@ static int forward_impl(const snfft_plan* p, const void* f, long long B, void* F
     void* nxt = (char*)ws + half;
     int rc;
     if ((rc = run_gather<T, false>(p, f, cur, B, st))) return rc;
-    for (int k = 2; k <= p->n; ++k) {
+    int k_first = 2;
+    const int base = g_no_base.load();          // 0: generated register kernels, 1: level kernels, 2: shared-memory base kernel
+    if (base == 0 && p->n > 5) {
+        if ((rc = run_s5<T, false>(p, cur, nxt, B, st))) return rc;
+        std::swap(cur, nxt);
+        k_first = 6;
+        if (p->n > 6) {
+            if ((rc = run_l6<T, false>(p, cur, nxt, B, st))) return rc;
+            std::swap(cur, nxt);
+            k_first = 7;
+        }
+    } else if (base == 2 && p->n > kBaseK0) {
+        if ((rc = run_base<T, false>(p, cur, nxt, B, st))) return rc;
+        std::swap(cur, nxt);
+        k_first = kBaseK0 + 1;
+    }
+    for (int k = k_first; k <= p->n; ++k) {
         void* out = (k == p->n) ? F : nxt;
         if ((rc = run_fwd_level<T>(p, k, cur, out, B, st))) return rc;
         std::swap(cur, nxt);
@@ -447,8 +594,26 @@ static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f
     const void* cur = F;
     void* bufs[2] = {ws, (char*)ws + half};
     int which = 0, rc;
-    for (int k = p->n; k >= 2; --k) {
+    const int base = g_no_base.load();
+    int k_last = 2;                             // lowest level the per-level kernels handle
+    if (base == 0 && p->n > 5) k_last = p->n > 6 ? 7 : 6;
+    else if (base == 2 && p->n > kBaseK0) k_last = kBaseK0 + 1;
+    for (int k = p->n; k >= k_last; --k) {
         if ((rc = run_inv_level<T>(p, k, cur, bufs[which], B, st))) return rc;
+        cur = bufs[which];
+        which ^= 1;
+    }
+    if (base == 0 && p->n > 5) {
+        if (p->n > 6) {
+            if ((rc = run_l6<T, true>(p, cur, bufs[which], B, st))) return rc;
+            cur = bufs[which];
+            which ^= 1;
+        }
+        if ((rc = run_s5<T, true>(p, cur, bufs[which], B, st))) return rc;
+        cur = bufs[which];
+        which ^= 1;
+    } else if (base == 2 && p->n > kBaseK0) {
+        if ((rc = run_base<T, true>(p, cur, bufs[which], B, st))) return rc;
         cur = bufs[which];
         which ^= 1;
     }
@@ -466,6 +631,45 @@ static IndexArgs make_index_args(int n) {
 }
 
 }  // namespace snfft
+
+template <typename T>
+static int dense_rep_impl(snfft_plan* p, int part, void* out, cudaStream_t st) {
+    const HostLevel& L = p->host.levels[p->n];
+    const int n = p->n;
+    if (!p->rt_partner) {            // first use: upload the per-row tables of level n
+        std::vector<int32_t> pt;
+        std::vector<T> dg, of;
+        p->rt_base.clear();
+        for (const HostShape& S : L.shapes) {
+            p->rt_base.push_back((long long)pt.size());
+            for (int j = 0; j <= n - 2; ++j)
+                for (int t = 0; t < S.dim; ++t) {
+                    pt.push_back(S.partner[j][t]);
+                    dg.push_back((T)S.diag[j][t]);
+                    of.push_back(S.partner[j][t] == t ? (T)0 : (T)S.off[j][t]);
+                }
+        }
+        int rc;
+        if ((rc = upload(p, pt, &p->rt_partner))) return rc;
+        if ((rc = upload(p, dg, &p->rt_diag))) return rc;
+        if ((rc = upload(p, of, &p->rt_off))) return rc;
+    }
+    const int d = L.shapes[part].dim;
+    RowTables<T> tb;
+    tb.partner = (const int*)p->rt_partner + p->rt_base[part];
+    tb.diag = (const T*)p->rt_diag + p->rt_base[part];
+    tb.off = (const T*)p->rt_off + p->rt_base[part];
+    const long long q = p->ia.nfact * d;
+    dim3 grid((unsigned)((q + 31) / 32), 1, 1), block(32, 1, 1);
+    auto kfn = dense_rep_kernel<T>;
+    const size_t smem = (size_t)2 * d * 32 * sizeof(T);
+    int rc;
+    if ((rc = set_smem(kfn, smem))) return rc;
+    SNFFT_LAUNCH(kfn, grid, block, smem, st, tb, d, (T*)out, p->ia);
+    g_launches.fetch_add(1);
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
+}
 
 // ---------------------------------------------------------------------------
 // extern "C"
@@ -487,6 +691,10 @@ int64_t snfft_launch_count(void) { return (int64_t)g_launches.load(); }
 // test hook: run every shape whose dimension fits in kernel class `cls` (0..5; -1 = automatic);
 // affects plans created afterwards.
 void snfft_debug_force_class(int cls) { g_force_class.store(cls); }
+
+// test hook: how levels 2..6 run.  0 = generated register kernels (default), 1 = per-level
+// table-driven kernels, 2 = table-driven shared-memory base kernel
+void snfft_debug_disable_base(int mode) { g_no_base.store(mode); }
 
 int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
     if (!out) return set_error(SNFFT_EINVAL, "out is NULL");
@@ -693,31 +901,14 @@ int snfft_chain_index(int n, int64_t* p1, void* stream) {
     return SNFFT_OK;
 }
 
-int snfft_dense_rep(const snfft_plan_t* p, int part, void* out, void* stream) {
+int snfft_dense_rep(snfft_plan_t* p, int part, void* out, void* stream) {
     if (!p || !out) return set_error(SNFFT_EINVAL, "NULL plan or output");
     const HostLevel& L = p->host.levels[p->n];
     if (part < 0 || part >= (int)L.shapes.size()) return set_error(SNFFT_EINVAL, "bad partition index");
-    const int d = L.shapes[part].dim;
-    const long long q = p->ia.nfact * d;
-    dim3 grid((unsigned)((q + 31) / 32), 1, 1), block(32, 1, 1);
+    if ((size_t)2 * L.shapes[part].dim * 32 * p->esize > 200 * 1024)
+        return set_error(SNFFT_ENOTSUP, "snfft_dense_rep: irrep too large for the dense cross-check");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (p->dtype == SNFFT_F32) {
-        const LevelArgs<float> a = level_args<float>(p, p->n, nullptr, nullptr, 1);
-        auto kfn = dense_rep_kernel<float>;
-        const size_t smem = (size_t)d * 32 * sizeof(float);
-        if ((rc = set_smem(kfn, smem))) return rc;
-        SNFFT_LAUNCH(kfn, grid, block, smem, st, a, part, d, (float*)out, p->ia);
-    } else {
-        const LevelArgs<double> a = level_args<double>(p, p->n, nullptr, nullptr, 1);
-        auto kfn = dense_rep_kernel<double>;
-        const size_t smem = (size_t)d * 32 * sizeof(double);
-        if ((rc = set_smem(kfn, smem))) return rc;
-        SNFFT_LAUNCH(kfn, grid, block, smem, st, a, part, d, (double*)out, p->ia);
-    }
-    g_launches.fetch_add(1);
-    SNFFT_CUDA(cudaGetLastError());
-    return SNFFT_OK;
+    return p->dtype == SNFFT_F32 ? dense_rep_impl<float>(p, part, out, st) : dense_rep_impl<double>(p, part, out, st);
 }
 
 int snfft_profile_begin(snfft_plan_t* p) {

@@ -147,14 +147,16 @@ int snfft_chain_index(int n, int64_t* p1_of_rank, void* stream);
  * matrix_representations (irreps.py:122-148); used by slow_sn_ft / slow_sn_ift
  * (fourier.py:82-108, 302-327).  n!*d*d elements: practical to n = 8.
  */
-int snfft_dense_rep(const snfft_plan_t* plan, int part, void* out, void* stream);
+int snfft_dense_rep(snfft_plan_t* plan, int part, void* out, void* stream);
 
 /*
  * Per-launch device timing with CUDA events on the launching stream.
  * Between snfft_profile_begin and snfft_profile_end every kernel this plan
  * launches is bracketed by an event pair; _end synchronises on them and returns
  * one aggregated record per (kind, level, kernel class).
- *   kind: 0 forward level, 1 inverse level, 2 input gather, 3 output scatter
+ *   kind: 0 forward level, 1 inverse level, 2 input gather, 3 output scatter,
+ *         4 forward base kernels (level = 5: levels 2..5 in registers; level = 6: level 6),
+ *         5 inverse base kernels (same levels)
  *   elems_per_instance: coefficients the launch produces per function
  *     (its share of k!; the launch reads as many), so its algorithmic traffic
  *     is 2 * elems_per_instance * NINST_level * sizeof(dtype) bytes.
@@ -174,6 +176,11 @@ int64_t snfft_launch_count(void);
  * class instead of the smallest fitting one; -1 restores the automatic choice.
  * Affects plans created afterwards.  Lets small n exercise every kernel class. */
 void snfft_debug_force_class(int cls);
+
+/* Test hook: how levels 2..6 run for n > 5.  0 = generated register kernels
+ * (default), 1 = per-level table-driven kernels, 2 = table-driven shared-memory
+ * base kernel; all three must agree, so every path stays covered. */
+void snfft_debug_disable_base(int mode);
 
 #ifdef __cplusplus
 }

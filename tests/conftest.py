@@ -43,7 +43,7 @@ def build_emu():
     if os.path.exists(EMU_SO) and all(os.path.getmtime(d) <= os.path.getmtime(EMU_SO) for d in deps):
         return EMU_SO
     os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O2", "-x", "c++", "-DSNFFT_HOST_EMU", "-I" + EMU_DIR, "-shared", "-fPIC",
+    cmd = ["g++", "-std=c++17", "-O1", "-x", "c++", "-DSNFFT_HOST_EMU", "-I" + EMU_DIR, "-shared", "-fPIC",
            "-o", EMU_SO] + srcs
     subprocess.run(cmd, check=True)
     return EMU_SO

@@ -25,6 +25,7 @@ inline dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __align__(x)
 
@@ -60,7 +61,7 @@ struct Sched {
     std::vector<char> done;
     const std::function<void()>* body = nullptr;
     int cur = 0;
-    static constexpr size_t kStack = 256 * 1024;
+    static constexpr size_t kStack = 64 * 1024;
 };
 inline Sched g;
 

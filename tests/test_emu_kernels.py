@@ -58,6 +58,30 @@ def test_every_kernel_class(emu, cls, dt):
         emu.snfft_plan_destroy(plan)
 
 
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("B", [1, 5, 37])
+def test_fused_base_kernel_equals_level_kernels(emu, dt, B):
+    """n = 7: levels 2..6 run in the fused shared-memory base kernel; the per-level path must agree."""
+    n = 7
+    rng = np.random.default_rng(B)
+    f = rng.standard_normal((B, math.factorial(n))).astype(DT[dt])
+    abi = CAbi(emu)
+    plan = abi.plan(n, DT[dt])
+    try:
+        fused = abi.forward(plan, f)
+        emu.snfft_debug_disable_base(1)
+        plain = abi.forward(plan, f)
+        assert np.array_equal(fused, plain)              # same arithmetic in the same order
+        inv_plain = abi.inverse(plan, fused, B)
+        emu.snfft_debug_disable_base(0)
+        inv_fused = abi.inverse(plan, fused, B)
+        assert np.array_equal(inv_fused, inv_plain)
+        assert rel_err(inv_fused, f) < TOL[dt]
+    finally:
+        emu.snfft_debug_disable_base(0)
+        emu.snfft_plan_destroy(plan)
+
+
 @pytest.mark.parametrize("B", [1, 2, 7, 33, 70])
 def test_ragged_batches(emu, B):
     n = 5
