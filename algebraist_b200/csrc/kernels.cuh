@@ -198,6 +198,13 @@ __device__ __forceinline__ const uint32_t* stage_table(uint32_t* tab_s, const ui
     return tab_s;
 }
 
+// 4/8-byte asynchronous global -> shared copy (LDGSTS): the fill of a work buffer
+// issues all its copies back to back instead of waiting on each load.
+template <typename T>
+__device__ __forceinline__ void copy_async(T* dst_smem, const T* src_global) {
+    SNFFT_CP_ASYNC(dst_smem, src_global, sizeof(T));
+}
+
 template <int G>
 __device__ __forceinline__ void group_sync() {
     if (G > 1) __syncthreads();
@@ -224,7 +231,10 @@ __device__ __forceinline__ SlotMap make_slots(bool packed, long long chunk, int 
     if (packed) {
         const long long ncx = (d_mu + cw - 1) / cw, nbx = (batch + ci - 1) / ci;
         *nchunks = ncx * nbx;
-        const long long cx = chunk % ncx, bx = chunk / ncx;
+        // neighbouring CTAs complete each other's partial sectors on the scattered side:
+        // the forward (packed output) walks columns first, the inverse (packed input) instances first
+        const long long cx = PACKED_IS_INPUT ? chunk / nbx : chunk % ncx;
+        const long long bx = PACKED_IS_INPUT ? chunk % nbx : chunk / ncx;
         // instance-fastest order: slot = c_rel * ci + i_rel ; column-fastest order: slot = i_rel * cw + c_rel
         const long long c_if = cx * cw + fs / ci, i_if = bx * ci + fs % ci;
         const long long c_cf = cx * cw + fs % cw, i_cf = bx * ci + fs / cw;
@@ -295,8 +305,12 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
             const bool inblk = sm.ok_ld && rr >= 0 && rr < tk.d_mu;
 #pragma unroll
             for (int m = 0; m < NBUF; ++m)
-                if (m < nb) work[m * bstride + t * TC + fs] = inblk ? src[rr * rstride + (i0 + m) * ninst] : T(0);
+                if (m < nb) {
+                    if (inblk) copy_async(work + m * bstride + t * TC + fs, src + rr * rstride + (i0 + m) * ninst);
+                    else work[m * bstride + t * TC + fs] = T(0);
+                }
         }
+        SNFFT_CP_ASYNC_WAIT();
         group_sync<G>();
         for (int j = k - 2; j >= i0; --j) {       // rho(s_i) ... rho(s_{k-2}) . work
             const int nact = (j - i0 + 1 < nb) ? (j - i0 + 1) : nb;
@@ -396,11 +410,14 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
         const uint32_t* __restrict__ tab = stage_table<STAGE>(reinterpret_cast<uint32_t*>(lut + 2 * LUT), a.tables,
                                                               par.tab_off, par.tab_words, tid, W * G * NG);
         for (int t = fr; t < par.d_lam; t += FR) {
-            const T x = sm.ok_ld ? src[t * rstride] : T(0);
 #pragma unroll
             for (int m = 0; m < NBUF; ++m)
-                if (m < nb) work[m * bstride + t * TC + fs] = x;
+                if (m < nb) {
+                    if (sm.ok_ld) copy_async(work + m * bstride + t * TC + fs, src + t * rstride);
+                    else work[m * bstride + t * TC + fs] = T(0);
+                }
         }
+        SNFFT_CP_ASYNC_WAIT();
         __syncthreads();
         for (int j = i0; j <= k - 2; ++j) {      // rho(c_i)^T = rho(s_{k-2}) ... rho(s_i)
             const int nact = (j - i0 + 1 < nb) ? (j - i0 + 1) : nb;

@@ -7,7 +7,14 @@
 #ifdef SNFFT_HOST_EMU
 #include "cuda_emu.h"
 #else
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
+#define SNFFT_CP_ASYNC(dst, src, bytes) __pipeline_memcpy_async(dst, src, bytes)
+#define SNFFT_CP_ASYNC_WAIT()      \
+    do {                           \
+        __pipeline_commit();       \
+        __pipeline_wait_prior(0);  \
+    } while (0)
 #define SNFFT_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
@@ -325,12 +332,22 @@ struct ProfScope {
     }
 };
 
-// cw x ci tile (columns x instances) of the packed-layout level, cw * ci == TC
-static void tile_shape(int TC, long long B, int* cw, int* ci) {
-    int c = 1;
-    while (c * 2 <= std::min(4, TC) && c * 2 <= B) c *= 2;
-    *ci = c;
-    *cw = TC / c;
+// cw x ci tile (columns x instances) of the packed-layout level, cw * ci == TC.
+// The side the kernel LOADS from gets a full 32-byte sector (8 fp32): instances for the forward
+// transform (its input is instance-fastest), columns for the inverse (its input is the packed
+// layout); the store side is completed by the neighbouring CTAs, which L2 merges.
+static void tile_shape(int TC, long long B, bool packed_is_input, int* cw, int* ci) {
+    if (packed_is_input) {
+        int w = std::min(8, TC);
+        while (TC / w > B && w < TC) w *= 2;      // few functions: widen the column side
+        *cw = w;
+        *ci = TC / w;
+    } else {
+        int c = 1;
+        while (c * 2 <= std::min(8, TC) && c * 2 <= B) c *= 2;
+        *ci = c;
+        *cw = TC / c;
+    }
 }
 
 template <typename KF>
@@ -350,7 +367,7 @@ static int launch_fwd_range(const TaskRange& r, bool final_level, LevelArgs<T> a
     constexpr int TC = V * W;
     long long chunks;
     if (final_level) {
-        tile_shape(TC, a.batch, &a.cw, &a.ci);
+        tile_shape(TC, a.batch, false, &a.cw, &a.ci);
         chunks = ((r.max_dmu + a.cw - 1) / a.cw) * ((a.batch + a.ci - 1) / a.ci);
     } else {
         a.cw = TC;
@@ -382,7 +399,7 @@ static int launch_inv_range(const TaskRange& r, bool first_level, LevelArgs<T> a
     constexpr int TC = V * W;
     long long chunks;
     if (first_level) {
-        tile_shape(TC, a.batch, &a.cw, &a.ci);
+        tile_shape(TC, a.batch, true, &a.cw, &a.ci);
         chunks = ((r.max_dmu + a.cw - 1) / a.cw) * ((a.batch + a.ci - 1) / a.ci);
     } else {
         a.cw = TC;

@@ -117,6 +117,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
 
 inline void __syncthreads() { emu::yield_barrier(); }
 
+#define SNFFT_CP_ASYNC(dst, src, bytes) std::memcpy(dst, src, bytes)
+#define SNFFT_CP_ASYNC_WAIT() ((void)0)
 #define SNFFT_DYN_SMEM(name) unsigned char* name = emu::dyn_smem
 #define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) \
     emu::launch(grid, block, smem, [&]() { kfn(__VA_ARGS__); })
