@@ -213,7 +213,10 @@ __device__ __forceinline__ void group_sync() {
 // Column tile bookkeeping shared by the forward and inverse kernels.
 // A tile is TC = W * V "slots"; a slot is one (column c, instance) pair of the
 // task's child block.  Threads have two roles:
-//   transfer role: slot fs = lt % TC, rows fr, fr + FR, ...   (global <-> shared, coalesced)
+//   transfer role: moves rows between global and shared memory.  Scalar form:
+//                  slot fs = lt % TC, rows fr, fr + FR, ...; vector form (intermediate
+//                  levels with NINST % TV == 0): TV = 16 / sizeof(T) adjacent slots
+//                  (= adjacent instances of one column, 16 aligned bytes) per thread.
 //   sweep role   : V slots lane*V.., rows / rotations rg, rg + G, ...
 // Intermediate levels enumerate slots instance-fastest over the flattened
 // (c, inst) range; the packed-layout level uses a cw x ci tile and two slot
@@ -266,16 +269,22 @@ template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, 
 __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelArgs<T> a) {
     SNFFT_DYN_SMEM(smem_raw);
     constexpr int TC = W * V, GT = W * G, FR = GT / TC;
+    constexpr int TV = 16 / (int)sizeof(T), NVS = TC / TV, FRV = GT / NVS;    // vector transfer role
     static_assert(G == 1 || NG == 1, "row groups need the whole CTA barrier");
-    static_assert(GT % TC == 0, "transfer role needs whole rows of threads");
+    static_assert(GT % TC == 0 && TC % TV == 0, "transfer role needs whole rows of threads");
     using P = Pack<T, V>;
+    using PV = Pack<T, TV>;
     const FwdTask tk = a.ftasks[blockIdx.y];
     const int tid = threadIdx.x;
     const int grp = tid / GT, lt = tid % GT, rg = lt / W, lane = lt % W;
-    const int fs = lt % TC, fr = lt / TC;
     const long long chunk = (long long)blockIdx.x * NG + grp;
     const int k = a.k;
     const long long ninst = a.ninst, ninst_prev = a.ninst * k;
+    // 16-byte transfers need alignment; with G == 1 nothing synchronises the lanes, so every
+    // thread may only touch its own slot (scalar role)
+    const bool vec = G > 1 && !FINAL && (ninst % TV == 0);
+    const int fs = vec ? (lt % NVS) * TV : lt % TC;     // first slot this thread transfers
+    const int fr = vec ? lt / NVS : lt / TC, frs = vec ? FRV : FR;
 
     long long nchunks;
     const SlotMap sm = make_slots<TC, false>(FINAL, chunk, fs, tk.d_mu, ninst, a.batch, a.cw, a.ci, &nchunks);
@@ -299,16 +308,49 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
 
     for (int i0 = 0; i0 < k; i0 += NBUF) {
         const int nb = (k - i0 < NBUF) ? (k - i0) : NBUF;
-        // work[m] <- embed_b( F^(i0+m)_mu[:, c] )
-        for (int t = fr; t < tk.d_lam; t += FR) {
-            const int rr = t - tk.boff;
-            const bool inblk = sm.ok_ld && rr >= 0 && rr < tk.d_mu;
+        // work[m] <- embed_b( F^(i0+m)_mu[:, c] ): zero rows outside the block, then the block rows
+        if (G > 1) {
+            PV zero;
 #pragma unroll
-            for (int m = 0; m < NBUF; ++m)
-                if (m < nb) {
-                    if (inblk) copy_async(work + m * bstride + t * TC + fs, src + rr * rstride + (i0 + m) * ninst);
-                    else work[m * bstride + t * TC + fs] = T(0);
+            for (int v = 0; v < TV; ++v) zero.v[v] = T(0);
+            const int zs = (lt % NVS) * TV;
+            for (int t = lt / NVS; t < tk.d_lam; t += FRV) {
+                const int rr = t - tk.boff;
+                if (rr >= 0 && rr < tk.d_mu && sm.ok_ld && vec) continue;      // filled by the copies below
+                if (rr >= 0 && rr < tk.d_mu && !vec) continue;
+#pragma unroll
+                for (int m = 0; m < NBUF; ++m)
+                    if (m < nb) *reinterpret_cast<PV*>(work + m * bstride + t * TC + zs) = zero;
+            }
+        } else {
+            for (int t = fr; t < tk.d_lam; t += FR) {
+                const int rr = t - tk.boff;
+                if (rr >= 0 && rr < tk.d_mu) continue;
+#pragma unroll
+                for (int m = 0; m < NBUF; ++m)
+                    if (m < nb) work[m * bstride + t * TC + fs] = T(0);
+            }
+        }
+        if (vec) {
+            if (sm.ok_ld) {
+                const T* __restrict__ p = src + (long long)fr * rstride + (long long)i0 * ninst;
+                T* __restrict__ w = work + (tk.boff + fr) * TC + fs;
+                for (int r = fr; r < tk.d_mu; r += FRV, p += (long long)FRV * rstride, w += FRV * TC) {
+#pragma unroll
+                    for (int m = 0; m < NBUF; ++m)
+                        if (m < nb) SNFFT_CP_ASYNC(w + m * bstride, p + m * ninst, 16);
                 }
+            }
+        } else {
+            for (int r = fr; r < tk.d_mu; r += FR) {
+#pragma unroll
+                for (int m = 0; m < NBUF; ++m)
+                    if (m < nb) {
+                        T* w = work + m * bstride + (tk.boff + r) * TC + fs;
+                        if (sm.ok_ld) copy_async(w, src + r * rstride + (i0 + m) * ninst);
+                        else *w = T(0);
+                    }
+            }
         }
         SNFFT_CP_ASYNC_WAIT();
         group_sync<G>();
@@ -348,7 +390,14 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
         } else {
             T* __restrict__ dst = a.out + (tk.lam_off + tk.boff + sm.c_st) * ninst + sm.inst_st;
             const long long ostride = (long long)tk.d_lam * ninst;
-            for (int t = fr; t < tk.d_lam; t += FR) dst[t * ostride] = work[t * TC + sm.src_slot];
+            if (vec) {
+                dst += (long long)fr * ostride;
+                const T* __restrict__ w = work + fr * TC + fs;
+                for (int t = fr; t < tk.d_lam; t += FRV, dst += (long long)FRV * ostride, w += FRV * TC)
+                    *reinterpret_cast<PV*>(dst) = *reinterpret_cast<const PV*>(w);
+            } else {
+                for (int t = fr; t < tk.d_lam; t += FR) dst[t * ostride] = work[t * TC + sm.src_slot];
+            }
         }
     }
 }
@@ -364,9 +413,11 @@ template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, 
 __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelArgs<T> a) {
     SNFFT_DYN_SMEM(smem_raw);
     constexpr int TC = W * V, GT = W * G, FR = GT / TC;
+    constexpr int TV = 16 / (int)sizeof(T), NVS = TC / TV, FRV = GT / NVS;
     static_assert(G == 1 || NG == 1, "row groups need the whole CTA barrier");
-    static_assert(GT % TC == 0, "transfer role needs whole rows of threads");
+    static_assert(GT % TC == 0 && TC % TV == 0, "transfer role needs whole rows of threads");
     using P = Pack<T, V>;
+    using PV = Pack<T, TV>;
     const InvTask tk = a.itasks[blockIdx.y];
     const int k = a.k;
     const int ngroups = (k + NBUF - 1) / NBUF;
@@ -374,10 +425,12 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
     const int nb = (k - i0 < NBUF) ? (k - i0) : NBUF;
     const int tid = threadIdx.x;
     const int grp = tid / GT, lt = tid % GT, rg = lt / W, lane = lt % W;
-    const int fs = lt % TC, fr = lt / TC;
     const long long cblock = blockIdx.x / ngroups;
     const long long chunk = cblock * NG + grp;
     const long long ninst = a.ninst, ninst_prev = a.ninst * k;
+    const bool vec = G > 1 && !FIRST && (ninst % TV == 0);
+    const int fs = vec ? (lt % NVS) * TV : lt % TC;
+    const int fr = vec ? lt / NVS : lt / TC;
 
     long long nchunks;
     const SlotMap sm = make_slots<TC, true>(FIRST, chunk, fs, tk.d_mu, ninst, a.batch, a.cw, a.ci, &nchunks);
@@ -409,13 +462,29 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
         }
         const uint32_t* __restrict__ tab = stage_table<STAGE>(reinterpret_cast<uint32_t*>(lut + 2 * LUT), a.tables,
                                                               par.tab_off, par.tab_words, tid, W * G * NG);
-        for (int t = fr; t < par.d_lam; t += FR) {
+        if (vec) {
+            PV zero;
 #pragma unroll
-            for (int m = 0; m < NBUF; ++m)
-                if (m < nb) {
-                    if (sm.ok_ld) copy_async(work + m * bstride + t * TC + fs, src + t * rstride);
-                    else work[m * bstride + t * TC + fs] = T(0);
-                }
+            for (int v = 0; v < TV; ++v) zero.v[v] = T(0);
+            const T* __restrict__ q = src + (long long)fr * rstride;
+            T* __restrict__ w = work + fr * TC + fs;
+            for (int t = fr; t < par.d_lam; t += FRV, q += (long long)FRV * rstride, w += FRV * TC) {
+#pragma unroll
+                for (int m = 0; m < NBUF; ++m)
+                    if (m < nb) {
+                        if (sm.ok_ld) SNFFT_CP_ASYNC(w + m * bstride, q, 16);
+                        else *reinterpret_cast<PV*>(w + m * bstride) = zero;
+                    }
+            }
+        } else {
+            for (int t = fr; t < par.d_lam; t += FR) {
+#pragma unroll
+                for (int m = 0; m < NBUF; ++m)
+                    if (m < nb) {
+                        if (sm.ok_ld) copy_async(work + m * bstride + t * TC + fs, src + t * rstride);
+                        else work[m * bstride + t * TC + fs] = T(0);
+                    }
+            }
         }
         SNFFT_CP_ASYNC_WAIT();
         __syncthreads();
@@ -458,7 +527,14 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
         for (int m = 0; m < NBUF; ++m)
             if (m < nb) {
                 T* __restrict__ dst = a.out + (tk.mu_off + sm.c_st) * ninst_prev + (long long)(i0 + m) * ninst + sm.inst_st;
-                for (int t = fr; t < tk.d_mu; t += FR) dst[t * ostride] = work[m * bstride + t * TC + sm.src_slot];
+                if (vec) {
+                    dst += (long long)fr * ostride;
+                    const T* __restrict__ w = work + m * bstride + fr * TC + fs;
+                    for (int t = fr; t < tk.d_mu; t += FRV, dst += (long long)FRV * ostride, w += FRV * TC)
+                        *reinterpret_cast<PV*>(dst) = *reinterpret_cast<const PV*>(w);
+                } else {
+                    for (int t = fr; t < tk.d_mu; t += FR) dst[t * ostride] = work[m * bstride + t * TC + sm.src_slot];
+                }
             }
     }
 }
