@@ -100,8 +100,8 @@ def _oracle_pair(args):
     import numpy as np
     from oracle import sn_oracle as O
     f = np.random.default_rng(seed).standard_normal((1, math.factorial(n))).astype(dtype)
-    ft = O.sn_fft_packed(f, n)
-    inv = O.sn_ifft_packed(ft, n)
+    ft = O.sn_fft_packed_c(f, n)           # oracle level steps with the C inner loops
+    inv = O.sn_ifft_packed_c(ft, n)
     return float(abs(inv - f).max())
 
 
@@ -128,10 +128,11 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 32))
     from oracle import sn_oracle as O
+    O.c_library()
     O.gather_index(a.n)                                  # tables warm (plan time, not step time)
-    for lam in O.generate_partitions(a.n):
-        for j in range(a.n - 1):
-            O.transposition_table(lam, j)
+    for k in range(2, a.n + 1):
+        for lam in O.generate_partitions(k):
+            O._c_tables(lam)
     sample = workers                                      # one function per worker per step
     times = []
     for s in range(a.warmup + a.steps):
@@ -146,7 +147,7 @@ def run_reference(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * total / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a), "n": a.n, "batch_per_gpu": a.batch,
-                   "note": "CPU oracle port of the reference algorithm (sparse YOR sweeps, numpy); the unmodified "
+                   "note": "CPU oracle port of the reference algorithm (sparse YOR sweeps, C inner loops); the unmodified "
                            "reference cannot run n >= 9 (SURVEY 0.3) and its recursive inverse raises for n > 5"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                          "sample": f"{sample} functions per step ({workers} processes x 1), forward+inverse"},
@@ -283,10 +284,17 @@ def run_native(a):
                     "path": "pinned host -> .to(cuda) -> sn_fft -> sn_ifft -> pinned host"},
         }
         if world == 1 and not a.no_cpu_baseline:
-            nfunc = 2 if n >= 10 else 8
+            nfunc = 4 if n >= 10 else 16
+            from oracle import sn_oracle as O
+            O.c_library()
+            for kk in range(2, n + 1):
+                for lam in O.generate_partitions(kk):
+                    O._c_tables(lam)
+            O.gather_index(n)
             v = cpu_pairs_per_s(n, a.dtype, nfunc, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{nfunc} functions of the same workload, forward+inverse, numpy oracle port"}
+                                    "sample": f"{nfunc} functions of the same workload, forward+inverse, "
+                                              "oracle port (sparse YOR sweeps, C inner loops, 1 thread)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
