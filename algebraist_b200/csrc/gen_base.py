@@ -16,7 +16,7 @@ Generated device functions (T = float / double):
 The combinatorics below restate the reference's conventions (partition order
 tableau.py:103-123, children irreps.py:64-68, basis order tableau.py:171-198,
 axial distance tableau.py:214-220); the generated code is checked against the
-oracle and the table-driven kernels by the test-suite.
+CPU restatement and the table-driven kernels by the test-suite.
 """
 import math
 import os

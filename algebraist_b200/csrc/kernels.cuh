@@ -114,7 +114,20 @@ __host__ __device__ inline long long rank_perm(int n, const int* sig, const long
 // at level k), p_1 = sum_k i_k * n!/k!.
 __host__ __device__ inline long long chain_index(int n, long long r, const long long* fact) {
     int sig[SNFFT_MAX_N];
-    unrank_perm(n, r, fact, sig);
+    if (n <= 12) {                       // n! < 2^31: 32-bit divisions are several times cheaper on the GPU
+        int vals[SNFFT_MAX_N];
+        unsigned rr = (unsigned)r;
+        for (int i = 0; i < n; ++i) vals[i] = i;
+        for (int i = 0; i < n; ++i) {
+            const unsigned f = (unsigned)fact[n - 1 - i];
+            const unsigned dgt = rr / f;
+            rr -= dgt * f;
+            sig[i] = vals[dgt];
+            for (int q = (int)dgt; q + 1 < n - i; ++q) vals[q] = vals[q + 1];
+        }
+    } else {
+        unrank_perm(n, r, fact, sig);
+    }
     long long p1 = 0;
     for (int k = n; k >= 2; --k) {
         const int v = k - 1;
@@ -702,12 +715,60 @@ __global__ void __launch_bounds__(GEN_THREADS) l6_kernel(const T* __restrict__ i
 }
 
 // ---------------------------------------------------------------------------
+// layout change of the top level: X_n instance-fastest [coef e][B]  <->  public
+// packed layout [lambda][B][d][d].  Per partition a [d^2][B] -> [B][d^2] tiled
+// transpose through shared memory.  grid (e-tiles * b-tiles, partitions)
+// ---------------------------------------------------------------------------
+constexpr int PK_T = 32;
+
+template <typename T, bool TO_PACKED>
+__global__ void __launch_bounds__(PK_T * 8) pack_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                         const long long* __restrict__ coef_off,
+                                                         const long long* __restrict__ tile_prefix, int nparts,
+                                                         long long batch) {
+    __shared__ T tile[PK_T][PK_T + 1];
+    // blockIdx.x = (global e-tile) * nbt + b-tile ; tile_prefix[l] = first e-tile of partition l
+    const long long nbt = (batch + PK_T - 1) / PK_T;
+    const long long etg = blockIdx.x / nbt, bt = blockIdx.x % nbt;
+    int lam = 0, hi = nparts - 1;
+    while (lam < hi) {
+        const int mid = (lam + hi + 1) / 2;
+        if (tile_prefix[mid] <= etg) lam = mid;
+        else hi = mid - 1;
+    }
+    const long long lo = coef_off[lam], dd = coef_off[lam + 1] - lo;
+    const long long et = etg - tile_prefix[lam];
+    const int tx = threadIdx.x % PK_T, ty = threadIdx.x / PK_T;       // 32 x 8
+    const long long e0 = et * PK_T, b0 = bt * PK_T;
+    // instance-fastest side: element (e, b) at (lo + e) * batch + b ; packed side: lo * batch + b * dd + e
+    for (int r = ty; r < PK_T; r += 8) {
+        if (TO_PACKED) {
+            const long long e = e0 + r, b = b0 + tx;
+            if (e < dd && b < batch) tile[r][tx] = in[(lo + e) * batch + b];
+        } else {
+            const long long b = b0 + r, e = e0 + tx;
+            if (e < dd && b < batch) tile[tx][r] = in[lo * batch + b * dd + e];
+        }
+    }
+    __syncthreads();
+    for (int r = ty; r < PK_T; r += 8) {
+        if (TO_PACKED) {
+            const long long b = b0 + r, e = e0 + tx;
+            if (e < dd && b < batch) out[lo * batch + b * dd + e] = tile[tx][r];
+        } else {
+            const long long e = e0 + r, b = b0 + tx;
+            if (e < dd && b < batch) out[(lo + e) * batch + b] = tile[r][tx];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // input gather / output scatter: the composition of restrict_to_coset over all
 // levels (fourier.py:253) as one tiled transpose.  grid (ranks/64, B/32), 256 thr
 //   GATHER :  x1[p1(r) * B + b] = f[b * n! + r]
 //   SCATTER:  f[b * n! + r]     = x1[p1(r) * B + b]
 // ---------------------------------------------------------------------------
-constexpr int GS_TR = 64, GS_TB = 32, GS_THREADS = 256;
+constexpr int GS_TR = 128, GS_TB = 32, GS_THREADS = 256;
 
 template <typename T>
 __host__ __device__ constexpr size_t gather_smem_bytes() {

@@ -119,6 +119,9 @@ struct snfft_plan {
     std::vector<DevLevel> lev;      // lev[k], k = 2..n
     std::vector<void*> allocs;      // every device allocation of the tables
     IndexArgs ia;
+    void* d_coef_off = nullptr;         // device copy of the level-n coefficient offsets (pack / unpack)
+    void* d_tile_prefix = nullptr;      // first 32-coefficient tile of every partition (pack / unpack grid)
+    long long n_pack_tiles = 0;
     // per-row YOR tables of level n for snfft_dense_rep, uploaded on first use
     void *rt_partner = nullptr, *rt_diag = nullptr, *rt_off = nullptr;
     std::vector<long long> rt_base;     // per partition: offset of its [n-1][d] block
@@ -380,11 +383,7 @@ static int launch_fwd_range(const TaskRange& r, bool final_level, LevelArgs<T> a
     const size_t smem = level_smem_bytes<T>(NG, NBUF, a.bstride, a.tab_smem_words);
     dim3 grid((unsigned)((chunks + NG - 1) / NG), (unsigned)r.count, 1), block(W * G * NG, 1, 1);
     int rc;
-    if (final_level) {
-        auto kfn = fwd_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, true>;
-        if ((rc = set_smem(kfn, smem))) return rc;
-        SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
-    } else {
+    {
         auto kfn = fwd_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, false>;
         if ((rc = set_smem(kfn, smem))) return rc;
         SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
@@ -413,11 +412,7 @@ static int launch_inv_range(const TaskRange& r, bool first_level, LevelArgs<T> a
     const long long ngroups = (a.k + NBUF - 1) / NBUF;      // coset groups, fastest grid dimension
     dim3 grid((unsigned)(((chunks + NG - 1) / NG) * ngroups), (unsigned)r.count, 1), block(W * G * NG, 1, 1);
     int rc;
-    if (first_level) {
-        auto kfn = inv_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, true>;
-        if ((rc = set_smem(kfn, smem))) return rc;
-        SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
-    } else {
+    {
         auto kfn = inv_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, false>;
         if ((rc = set_smem(kfn, smem))) return rc;
         SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
@@ -451,7 +446,7 @@ static LevelArgs<T> level_args(const snfft_plan* p, int k, const void* in, void*
 template <typename T>
 static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st) {
     const LevelArgs<T> a = level_args<T>(p, k, in, out, B);
-    const bool fin = (k == p->n);
+    const bool fin = false;      // the top level is instance-fastest too; pack_kernel converts it
     for (const TaskRange& r : p->lev[k].franges) {
         int rc = SNFFT_ENOTSUP;
         ProfScope prof(p, st, 0, k, r.cls, r.elems);
@@ -473,7 +468,7 @@ static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, 
 template <typename T>
 static int run_inv_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st) {
     const LevelArgs<T> a = level_args<T>(p, k, in, out, B);
-    const bool first = (k == p->n);
+    const bool first = false;    // unpack_kernel has already made the input instance-fastest
     for (const TaskRange& r : p->lev[k].iranges) {
         int rc = SNFFT_ENOTSUP;
         ProfScope prof(p, st, 1, k, r.cls, r.elems);
@@ -549,6 +544,21 @@ static int run_base(const snfft_plan* p, const void* in, void* out, long long B,
     return SNFFT_OK;
 }
 
+// X_n instance-fastest <-> packed [lambda][B][d][d]
+template <typename T, bool TO_PACKED>
+static int run_pack(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
+    const HostLevel& L = p->host.levels[p->n];
+    const long long tiles = p->n_pack_tiles * ((B + PK_T - 1) / PK_T);
+    dim3 grid((unsigned)tiles, 1, 1), block(PK_T * 8, 1, 1);
+    ProfScope prof(p, st, TO_PACKED ? 6 : 7, p->n, -1, p->host.factorial[p->n]);
+    auto kfn = pack_kernel<T, TO_PACKED>;
+    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)in, (T*)out, (const long long*)p->d_coef_off,
+                 (const long long*)p->d_tile_prefix, (int)L.shapes.size(), B);
+    g_launches.fetch_add(1);
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
+}
+
 // Generated register kernels: levels 2..5 of every S_5 instance, and level 6.
 template <typename T, bool INVERSE>
 static int run_s5(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
@@ -598,19 +608,19 @@ static int forward_impl(const snfft_plan* p, const void* f, long long B, void* F
         k_first = kBaseK0 + 1;
     }
     for (int k = k_first; k <= p->n; ++k) {
-        void* out = (k == p->n) ? F : nxt;
-        if ((rc = run_fwd_level<T>(p, k, cur, out, B, st))) return rc;
+        if ((rc = run_fwd_level<T>(p, k, cur, nxt, B, st))) return rc;
         std::swap(cur, nxt);
     }
-    return SNFFT_OK;
+    return run_pack<T, true>(p, cur, F, B, st);
 }
 
 template <typename T>
 static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f, void* ws, cudaStream_t st) {
     const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
-    const void* cur = F;
     void* bufs[2] = {ws, (char*)ws + half};
-    int which = 0, rc;
+    int which = 1, rc;
+    if ((rc = run_pack<T, false>(p, F, bufs[0], B, st))) return rc;
+    const void* cur = bufs[0];
     const int base = g_no_base.load();
     int k_last = 2;                             // lowest level the per-level kernels handle
     if (base == 0 && p->n > 5) k_last = p->n > 6 ? 7 : 6;
@@ -729,6 +739,23 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
         build_host_plan(n, p->host);
         p->ia = make_index_args(n);
         p->lev.resize(n + 1);
+        {
+            const HostLevel& L = p->host.levels[n];
+            std::vector<long long> offs(L.coef_offsets.begin(), L.coef_offsets.end());
+            std::vector<long long> pre;
+            long long t = 0;
+            for (const HostShape& S : L.shapes) {
+                pre.push_back(t);
+                t += ((long long)S.dim * S.dim + PK_T - 1) / PK_T;
+            }
+            p->n_pack_tiles = t;
+            int rc = upload(p, offs, &p->d_coef_off);
+            if (!rc) rc = upload(p, pre, &p->d_tile_prefix);
+            if (rc) {
+                snfft_plan_destroy(p);
+                return rc;
+            }
+        }
         for (int k = 2; k <= n; ++k) {
             const int rc = dtype == SNFFT_F32 ? build_level<float>(p, k) : build_level<double>(p, k);
             if (rc) {

@@ -251,11 +251,12 @@ def run_native(a):
 
     if rank == 0:
         peak, peak_src = peaks()
-        kinds = {0: "fwd_level", 1: "inv_level", 2: "gather", 3: "scatter", 4: "fwd_base", 5: "inv_base"}
+        kinds = {0: "fwd_level", 1: "inv_level", 2: "gather", 3: "scatter", 4: "fwd_base", 5: "inv_base",
+                 6: "pack", 7: "unpack"}
         kernels = []
         for i in range(nrec.value):
             r = recs[i]
-            ninst = B * (nf // math.factorial(r.level)) if r.kind in (0, 1, 4, 5) else B
+            ninst = B * (nf // math.factorial(r.level)) if r.kind in (0, 1, 4, 5, 6, 7) else B
             bytes_per_launch = 2 * r.elems_per_instance * ninst * esize
             avg_ms = r.total_ms / r.launches
             kernels.append({"kernel": f"{kinds[r.kind]}_k{r.level}_c{r.kernel_class}", "launches": r.launches,

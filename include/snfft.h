@@ -156,7 +156,7 @@ int snfft_dense_rep(snfft_plan_t* plan, int part, void* out, void* stream);
  * one aggregated record per (kind, level, kernel class).
  *   kind: 0 forward level, 1 inverse level, 2 input gather, 3 output scatter,
  *         4 forward base kernels (level = 5: levels 2..5 in registers; level = 6: level 6),
- *         5 inverse base kernels (same levels)
+ *         5 inverse base kernels (same levels), 6 pack (top level -> [lambda][B][d][d]), 7 unpack
  *   elems_per_instance: coefficients the launch produces per function
  *     (its share of k!; the launch reads as many), so its algorithmic traffic
  *     is 2 * elems_per_instance * NINST_level * sizeof(dtype) bytes.

@@ -21,6 +21,7 @@ struct dim3 {
 
 inline dim3 threadIdx, blockIdx, blockDim, gridDim;
 
+#define __shared__ static
 #define __global__
 #define __device__
 #define __host__
