@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "snfft.cu"), os.path.join(HERE, "csrc", "plan.cpp")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "plan.h")] + [
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "plan.h", "level_tb.cuh", "bot_gen.cuh", "base_gen.cuh", "tb_host.inl")] + [
     os.path.join(HERE, "..", "include", "snfft.h")]
 OUT = os.path.join(HERE, "libsnfft_b200.so")
 

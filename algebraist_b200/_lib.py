@@ -55,6 +55,7 @@ SIGNATURES = {
     "snfft_launch_count": (c_i64, []),
     "snfft_debug_force_class": (None, [c_int]),
     "snfft_debug_disable_base": (None, [c_int]),
+    "snfft_debug_tb_mode": (None, [c_int]),
 }
 
 

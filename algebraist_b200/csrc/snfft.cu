@@ -20,9 +20,11 @@
 #endif
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <stdexcept>
@@ -30,6 +32,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "level_tb.cuh"
 #include "plan.h"
 
 namespace snfft {
@@ -61,6 +64,7 @@ static const int kNumClasses = 6;
 
 static std::atomic<int> g_force_class{-1};
 static std::atomic<int> g_no_base{0};
+static std::atomic<int> g_tb_mode{-1};      // -1 automatic, 0 sweep-per-pass kernels only, 1..3 force s fused top sweeps
 static std::atomic<long long> g_launches{0};
 static thread_local std::string g_error;
 
@@ -92,7 +96,17 @@ struct TaskRange {
     long long elems;      // coefficients this launch produces per instance (its share of k!)
 };
 
+struct TbRange {          // one launch of the TB kernels: tasks that share a tile width
+    int tcl, nt, begin, count, max_dmu, max_dlam, max_tt, max_ct, max_bt;
+    long long elems;
+};
+
 struct DevLevel {
+    // TB kernels (level_tb.cuh): tb_s = 0 means the level runs the sweep-per-pass kernels
+    int tb_s = 0;
+    bool tb_fwd = false, tb_inv = false;      // which directions use them (the other runs the sweep kernels)
+    void *tb_tasks = nullptr, *tb_itasks = nullptr, *tb_tt = nullptr, *tb_ct = nullptr, *tb_bt = nullptr;
+    std::vector<TbRange> tb_franges, tb_iranges;
     void* tables = nullptr;
     void *ftasks = nullptr, *itasks = nullptr, *parents = nullptr;
     int nftasks = 0, nitasks = 0, tab_words = 0;
@@ -365,6 +379,8 @@ static int set_smem(KF kfn, size_t bytes) {
     return SNFFT_OK;
 }
 
+#include "tb_host.inl"
+
 template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE>
 static int launch_fwd_range(const TaskRange& r, bool final_level, LevelArgs<T> a, cudaStream_t st) {
     constexpr int TC = V * W;
@@ -608,7 +624,9 @@ static int forward_impl(const snfft_plan* p, const void* f, long long B, void* F
         k_first = kBaseK0 + 1;
     }
     for (int k = k_first; k <= p->n; ++k) {
-        if ((rc = run_fwd_level<T>(p, k, cur, nxt, B, st))) return rc;
+        if (p->lev[k].tb_s > 0 && p->lev[k].tb_fwd) rc = run_tb_level<T, false>(p, k, cur, nxt, B, st);
+        else rc = run_fwd_level<T>(p, k, cur, nxt, B, st);
+        if (rc) return rc;
         std::swap(cur, nxt);
     }
     return run_pack<T, true>(p, cur, F, B, st);
@@ -626,7 +644,9 @@ static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f
     if (base == 0 && p->n > 5) k_last = p->n > 6 ? 7 : 6;
     else if (base == 2 && p->n > kBaseK0) k_last = kBaseK0 + 1;
     for (int k = p->n; k >= k_last; --k) {
-        if ((rc = run_inv_level<T>(p, k, cur, bufs[which], B, st))) return rc;
+        if (p->lev[k].tb_s > 0 && p->lev[k].tb_inv) rc = run_tb_level<T, true>(p, k, cur, bufs[which], B, st);
+        else rc = run_inv_level<T>(p, k, cur, bufs[which], B, st);
+        if (rc) return rc;
         cur = bufs[which];
         which ^= 1;
     }
@@ -722,6 +742,7 @@ void snfft_debug_force_class(int cls) { g_force_class.store(cls); }
 // test hook: how levels 2..6 run.  0 = generated register kernels (default), 1 = per-level
 // table-driven kernels, 2 = table-driven shared-memory base kernel
 void snfft_debug_disable_base(int mode) { g_no_base.store(mode); }
+void snfft_debug_tb_mode(int mode) { g_tb_mode.store(mode); }
 
 int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
     if (!out) return set_error(SNFFT_EINVAL, "out is NULL");
@@ -757,7 +778,18 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
             }
         }
         for (int k = 2; k <= n; ++k) {
-            const int rc = dtype == SNFFT_F32 ? build_level<float>(p, k) : build_level<double>(p, k);
+            int rc = dtype == SNFFT_F32 ? build_level<float>(p, k) : build_level<double>(p, k);
+            const int s = tb_pick_s(k);
+            if (!rc && s > 0 && k - s >= 3) {
+                rc = dtype == SNFFT_F32 ? build_tb_level<float>(p, k, s) : build_tb_level<double>(p, k, s);
+                tb_pick_dirs(k, dtype, &p->lev[k].tb_fwd, &p->lev[k].tb_inv);
+                if (rc == SNFFT_ENOTSUP) {          // shapes too large for the TB tiles: keep the sweep kernels
+                    p->lev[k].tb_s = 0;
+                    p->lev[k].tb_franges.clear();
+                    p->lev[k].tb_iranges.clear();
+                    rc = SNFFT_OK;
+                }
+            }
             if (rc) {
                 snfft_plan_destroy(p);
                 return rc;

@@ -277,7 +277,7 @@ def run_native(a):
                          "peak_source": peak_src, "kernel_share_of_step": top["share"],
                          "end_to_end_alg_gbs": value / world * alg_bytes_pair / 1e9,
                          "end_to_end_frac": value / world * alg_bytes_pair / 1e9 / peak},
-            "kernels": kernels[:16],
+            "kernels": kernels[:40],
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * nf * esize,

@@ -182,6 +182,14 @@ void snfft_debug_force_class(int cls);
  * base kernel; all three must agree, so every path stays covered. */
 void snfft_debug_disable_base(int mode);
 
+/* Test hook: which kernels run the level steps k >= 7 (and every level when the
+ * base kernels are disabled).  -1 = automatic (fused-top / register-bottom "TB"
+ * kernels with s = 1, 1, 2, 3 fused sweeps at k = 7, 8, 9, 10, sweep-per-pass
+ * kernels elsewhere), 0 = sweep-per-pass kernels only, 1..3 = TB kernels with
+ * that many fused top sweeps wherever such a kernel is compiled.  Affects plans
+ * created afterwards; both families must agree with the oracle. */
+void snfft_debug_tb_mode(int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,8 @@ def load_transform_golden(n):
 def build_emu():
     """g++ build of the CUDA sources against tests/emu/cuda_emu.h (tests only)."""
     srcs = [os.path.join(CSRC, "snfft.cu"), os.path.join(CSRC, "plan.cpp")]
-    deps = srcs + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "plan.h"),
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h", "level_tb.cuh", "bot_gen.cuh",
+                                                   "base_gen.cuh", "tb_host.inl")] + [
                    os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "snfft.h")]
     if os.path.exists(EMU_SO) and all(os.path.getmtime(d) <= os.path.getmtime(EMU_SO) for d in deps):
         return EMU_SO

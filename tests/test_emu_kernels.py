@@ -156,3 +156,57 @@ def test_launch_counter(emu):
     abi.forward(plan, np.zeros((1, 24), dtype=np.float32))
     emu.snfft_plan_destroy(plan)
     assert emu.snfft_launch_count() - before >= 4      # gather + levels 2..4
+
+
+# (n, tb mode, base mode): which fused-top / register-bottom ("TB") kernel the level steps run.
+# mode -1 is the product's automatic choice, 0 the sweep-per-pass kernels, 1..3 force s fused top sweeps;
+# base 1 sends the levels <= 6 through the level kernels too, so small n reaches every (MB, s) combination.
+TB_CASES = [(7, -1, 0), (7, 2, 0), (7, 3, 0), (6, 1, 1), (6, 2, 1), (6, 3, 1), (5, 1, 1), (8, -1, 0), (8, 2, 0),
+            (8, 3, 0)]
+
+
+@pytest.mark.parametrize("n,mode,base", TB_CASES)
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_tb_kernels_vs_oracle(emu, n, mode, base, dt):
+    """Fused-top / register-bottom level kernels (level_tb.cuh) against the oracle, forward and inverse."""
+    B = 1 if n == 8 else 3
+    rng = np.random.default_rng(10 * n + mode)
+    f = rng.standard_normal((B, math.factorial(n))).astype(DT[dt])
+    emu.snfft_debug_tb_mode(mode)
+    emu.snfft_debug_disable_base(base)
+    abi = CAbi(emu)
+    plan = abi.plan(n, DT[dt])
+    emu.snfft_debug_tb_mode(-1)
+    try:
+        packed = abi.forward(plan, f)
+        ref = O.sn_fft_packed(f.astype(np.float64), n)
+        ft = unpack(packed, n, B)
+        for lam in ref:
+            assert rel_err(ft[lam], ref[lam]) < TOL[dt], lam
+        coef = {lam: rng.standard_normal(v.shape) for lam, v in ref.items()}
+        got = abi.inverse(plan, pack(coef, n, B, DT[dt]), B)
+        assert rel_err(got, O.sn_ifft_packed(coef, n)) < TOL[dt]
+        assert rel_err(abi.inverse(plan, packed, B), f) < TOL[dt]
+    finally:
+        emu.snfft_debug_disable_base(0)
+        emu.snfft_plan_destroy(plan)
+
+
+def test_tb_and_sweep_kernels_agree_ragged_batch(emu):
+    """Odd batch (scalar transfer path, ragged last tile): both kernel families give the same coefficients."""
+    n, B = 7, 5
+    rng = np.random.default_rng(7)
+    f = rng.standard_normal((B, math.factorial(n)))
+    outs = []
+    for mode in (0, 1, 3):
+        emu.snfft_debug_tb_mode(mode)
+        abi = CAbi(emu)
+        plan = abi.plan(n, np.float64)
+        emu.snfft_debug_tb_mode(-1)
+        try:
+            packed = abi.forward(plan, f)
+            outs.append(packed)
+            assert rel_err(abi.inverse(plan, packed, B), f) < 1e-12
+        finally:
+            emu.snfft_plan_destroy(plan)
+    assert rel_err(outs[1], outs[0]) < 1e-13 and rel_err(outs[2], outs[0]) < 1e-13

@@ -218,3 +218,29 @@ def test_cpu_tensor_round_trip_and_streams(A):
 def test_empty_batch(A):
     ft = A.sn_fft(torch.empty(0, 120, device="cuda"), 5)
     assert tuple(ft[(5,)].shape) == (0,) and tuple(ft[(3, 2)].shape) == (0, 5, 5)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_kernel_families_vs_oracle(A, mode, dt):
+    """Level steps 7..10 through the sweep-per-pass kernels (mode 0) and through the fused-top /
+    register-bottom kernels with s = 1, 2, 3 fused sweeps (levels 7-8, 9, 10), forward and inverse."""
+    from algebraist_b200 import plan as P
+    n, B = 10, 2
+    lib = A._lib.load()
+    rng = np.random.default_rng(1000 + mode)
+    f = rng.standard_normal((B, math.factorial(n)))
+    ref = O.sn_fft_packed(f, n)
+    lib.snfft_debug_tb_mode(mode)
+    saved = dict(P._cache)
+    P._cache.clear()
+    try:
+        x = torch.from_numpy(f).to(TDT[dt]).cuda()
+        ft = A.sn_fft(x, n)
+        _check_dict(ft, ref, TOL[dt])
+        inv = A.sn_ifft(ft, n)
+        assert rel_err(inv.cpu().numpy(), f) < TOL[dt]
+    finally:
+        lib.snfft_debug_tb_mode(-1)
+        P._cache.clear()
+        P._cache.update(saved)
