@@ -63,6 +63,11 @@ struct LevelArgs {
     int tab_smem_words;           // shared-memory words reserved for one task table
     long long ninst;              // NINST_k
     long long batch;              // B
+    // forward only: the chains (cosets of S_{k-1}) that are present.  The input holds nch planes per
+    // coefficient (plane j = coset cid[j], ascending); the missing cosets contribute nothing.  A full
+    // step has nch = k, cid[j] = j; the coset-sharded transform passes the cosets one rank owns.
+    int nch;
+    int cid[SNFFT_MAX_N];
     T lut[2 * LUT];
 };
 
@@ -291,8 +296,8 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
     const int tid = threadIdx.x;
     const int grp = tid / GT, lt = tid % GT, rg = lt / W, lane = lt % W;
     const long long chunk = (long long)blockIdx.x * NG + grp;
-    const int k = a.k;
-    const long long ninst = a.ninst, ninst_prev = a.ninst * k;
+    const int k = a.k, nch = a.nch;
+    const long long ninst = a.ninst, ninst_prev = a.ninst * nch;
     // 16-byte transfers need alignment; with G == 1 nothing synchronises the lanes, so every
     // thread may only touch its own slot (scalar role)
     const bool vec = G > 1 && !FINAL && (ninst % TV == 0);
@@ -319,9 +324,9 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[q].v[v] = T(0);
 
-    for (int i0 = 0; i0 < k; i0 += NBUF) {
-        const int nb = (k - i0 < NBUF) ? (k - i0) : NBUF;
-        // work[m] <- embed_b( F^(i0+m)_mu[:, c] ): zero rows outside the block, then the block rows
+    for (int i0 = 0; i0 < nch; i0 += NBUF) {      // i0: first plane of the group; its coset is a.cid[i0]
+        const int nb = (nch - i0 < NBUF) ? (nch - i0) : NBUF;
+        // work[m] <- embed_b( F^(cid[i0+m])_mu[:, c] ): zero rows outside the block, then the block rows
         if (G > 1) {
             PV zero;
 #pragma unroll
@@ -367,8 +372,11 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
         }
         SNFFT_CP_ASYNC_WAIT();
         group_sync<G>();
-        for (int j = k - 2; j >= i0; --j) {       // rho(s_i) ... rho(s_{k-2}) . work
-            const int nact = (j - i0 + 1 < nb) ? (j - i0 + 1) : nb;
+        for (int j = k - 2; j >= a.cid[i0]; --j) {       // rho(s_i) ... rho(s_{k-2}) . work, i = cid[i0 + m] <= j
+            int nact = 1;
+#pragma unroll
+            for (int m = 1; m < NBUF; ++m)
+                if (m < nb && a.cid[i0 + m] <= j) nact = m + 1;
             sweep<T, V, TC, G, NBUF>(work, bstride, nact, tab, lut, k, j, rg, lane);
             group_sync<G>();
         }
@@ -854,6 +862,37 @@ __global__ void coset_index_kernel(int coset, long long* __restrict__ idx, const
         out += lj * ia.fact[n - 1 - pos];
     }
     idx[r] = out;
+}
+
+// restrict_to_coset (fourier.py:63-80) for a list of cosets and a batch of functions:
+//   out[(j * B + b) * (n-1)! + r'] = f[b * n! + idx_{coset[j]}(r')],  idx = the closed form of coset_index_kernel.
+// The (j, b) order makes the planes of the next level step contiguous (plane j = coset[j], B instances each).
+struct RestrictArgs {
+    IndexArgs ia;
+    long long batch;
+    int ncos;
+    int coset[SNFFT_MAX_N];
+};
+
+template <typename T>
+__global__ void restrict_kernel(const T* __restrict__ f, T* __restrict__ out, const RestrictArgs ra) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = ra.ia.n;
+    const long long fm = ra.ia.fact[n - 1];
+    if (e >= (long long)ra.ncos * ra.batch * fm) return;
+    const long long r = e % fm, jb = e / fm;
+    const long long b = jb % ra.batch;
+    const int coset = ra.coset[jb / ra.batch];
+    long long src = (long long)(n - 1 - coset) * ra.ia.fact[n - 1 - coset];
+    long long rem = r;
+    for (int j = 0; j < n - 1; ++j) {
+        const long long fj = ra.ia.fact[n - 2 - j];
+        const long long lj = rem / fj;
+        rem -= lj * fj;
+        const int pos = j < coset ? j : j + 1;
+        src += lj * ra.ia.fact[n - 1 - pos];
+    }
+    out[e] = f[b * ra.ia.nfact + src];
 }
 
 __global__ void chain_index_kernel(long long* __restrict__ p1, const IndexArgs ia) {

@@ -456,12 +456,20 @@ static LevelArgs<T> level_args(const snfft_plan* p, int k, const void* in, void*
     a.cw = a.ci = a.bstride = a.tab_smem_words = 0;
     a.ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
     a.batch = B;
+    a.nch = k;
+    for (int j = 0; j < SNFFT_MAX_N; ++j) a.cid[j] = j;
     return a;
 }
 
+// nch > 0: only the cosets cid[0..nch) (ascending) are present in `in` (nch planes per coefficient)
 template <typename T>
-static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st) {
-    const LevelArgs<T> a = level_args<T>(p, k, in, out, B);
+static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st,
+                         int nch = 0, const int* cid = nullptr) {
+    LevelArgs<T> a = level_args<T>(p, k, in, out, B);
+    if (nch > 0) {
+        a.nch = nch;
+        for (int j = 0; j < nch; ++j) a.cid[j] = cid[j];
+    }
     const bool fin = false;      // the top level is instance-fastest too; pack_kernel converts it
     for (const TaskRange& r : p->lev[k].franges) {
         int rc = SNFFT_ENOTSUP;
@@ -600,8 +608,11 @@ static int run_l6(const snfft_plan* p, const void* in, void* out, long long B, c
     return SNFFT_OK;
 }
 
+static IndexArgs make_index_args(int n);
+
+// levels 1..n of the forward pipeline; *result points at X_n (instance fastest) inside the workspace
 template <typename T>
-static int forward_impl(const snfft_plan* p, const void* f, long long B, void* F, void* ws, cudaStream_t st) {
+static int forward_levels(const snfft_plan* p, const void* f, long long B, void* ws, cudaStream_t st, void** result) {
     const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
     void* cur = ws;
     void* nxt = (char*)ws + half;
@@ -629,7 +640,51 @@ static int forward_impl(const snfft_plan* p, const void* f, long long B, void* F
         if (rc) return rc;
         std::swap(cur, nxt);
     }
-    return run_pack<T, true>(p, cur, F, B, st);
+    *result = cur;
+    return SNFFT_OK;
+}
+
+template <typename T>
+static int forward_impl(const snfft_plan* p, const void* f, long long B, void* F, void* ws, cudaStream_t st) {
+    void* xn = nullptr;
+    const int rc = forward_levels<T>(p, f, B, ws, st, &xn);
+    if (rc) return rc;
+    return run_pack<T, true>(p, xn, F, B, st);
+}
+
+// Partial forward transform over a subset of the top-level cosets {sigma : sigma[i] = n-1}:
+//   F_partial(lambda) = sum_{i in cosets} rho_lambda(c_i) . blockdiag_mu F^(i)_mu      (fourier.py:253-273)
+// so that the sum of F_partial over a partition of range(n) is the full transform.  The restricted functions
+// f^(i) (restrict_to_coset, fourier.py:63-80) go through the S_{n-1} plan as one batch of ncos * B functions.
+// workspace: [restricted input][S_{n-1} pipeline scratch][X_n]
+template <typename T>
+static int forward_cosets_impl(const snfft_plan* pn, const snfft_plan* pm, const void* f, long long B, const int* cosets,
+                               int ncos, void* F, void* ws, cudaStream_t st) {
+    const int n = pn->n;
+    const long long fm = pn->host.factorial[n - 1], fn = pn->host.factorial[n];
+    const long long Bm = (long long)ncos * B;
+    T* rin = (T*)ws;
+    void* wsm = (char*)ws + (size_t)Bm * fm * sizeof(T);
+    T* xn = (T*)((char*)wsm + snfft_workspace_bytes(pm, Bm));
+    {
+        const long long total = Bm * fm;
+        RestrictArgs ra;
+        ra.ia = make_index_args(n);
+        ra.batch = B;
+        ra.ncos = ncos;
+        for (int j = 0; j < ncos; ++j) ra.coset[j] = cosets[j];
+        dim3 grid((unsigned)((total + 255) / 256), 1, 1), block(256, 1, 1);
+        auto kfn = restrict_kernel<T>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)f, rin, ra);
+        g_launches.fetch_add(1);
+        SNFFT_CUDA(cudaGetLastError());
+    }
+    void* xm = nullptr;
+    int rc = forward_levels<T>(pm, rin, Bm, wsm, st, &xm);
+    if (rc) return rc;
+    if ((rc = run_fwd_level<T>(pn, n, xm, xn, B, st, ncos, cosets))) return rc;
+    (void)fn;
+    return run_pack<T, true>(pn, xn, F, B, st);
 }
 
 template <typename T>
@@ -871,6 +926,37 @@ int snfft_forward(const snfft_plan_t* p, const void* f, int64_t B, void* F, void
     if (rc || B == 0) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     return p->dtype == SNFFT_F32 ? forward_impl<float>(p, f, B, F, ws, st) : forward_impl<double>(p, f, B, F, ws, st);
+}
+
+size_t snfft_forward_cosets_workspace_bytes(const snfft_plan_t* pn, const snfft_plan_t* pm, int64_t B, int ncosets) {
+    if (!pn || !pm || B < 0 || ncosets < 0) return 0;
+    const size_t Bm = (size_t)B * (size_t)ncosets;
+    return Bm * (size_t)pm->host.factorial[pm->n] * pm->esize + snfft_workspace_bytes(pm, (int64_t)Bm) +
+           (size_t)B * (size_t)pn->host.factorial[pn->n] * pn->esize;
+}
+
+int snfft_forward_cosets(const snfft_plan_t* pn, const snfft_plan_t* pm, const void* f, int64_t B, const int* cosets,
+                         int ncosets, void* F, void* ws, size_t ws_bytes, void* stream) {
+    if (!pn || !pm) return set_error(SNFFT_EINVAL, "plan is NULL");
+    if (pm->n != pn->n - 1 || pm->dtype != pn->dtype || pm->device != pn->device)
+        return set_error(SNFFT_EINVAL, "the second plan must be the S_{n-1} plan of the same dtype and device");
+    if (pn->n < 3) return set_error(SNFFT_EINVAL, "coset sharding needs n >= 3");
+    if (B < 0 || ncosets < 0 || ncosets > pn->n) return set_error(SNFFT_EINVAL, "bad batch or coset count");
+    if (B == 0) return SNFFT_OK;
+    if (!f || !F || (ncosets && !cosets)) return set_error(SNFFT_EINVAL, "NULL data pointer");
+    for (int j = 0; j < ncosets; ++j)
+        if (cosets[j] < 0 || cosets[j] >= pn->n || (j > 0 && cosets[j] <= cosets[j - 1]))
+            return set_error(SNFFT_EINVAL, "cosets must be strictly ascending indices in [0, n)");
+    const size_t out_bytes = (size_t)B * (size_t)pn->host.factorial[pn->n] * pn->esize;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ncosets == 0) {              // a rank that owns nothing contributes zero
+        SNFFT_CUDA(cudaMemsetAsync(F, 0, out_bytes, st));
+        return SNFFT_OK;
+    }
+    if (!ws || ws_bytes < snfft_forward_cosets_workspace_bytes(pn, pm, B, ncosets))
+        return set_error(SNFFT_EWORKSPACE, "workspace too small");
+    return pn->dtype == SNFFT_F32 ? forward_cosets_impl<float>(pn, pm, f, B, cosets, ncosets, F, ws, st)
+                                  : forward_cosets_impl<double>(pn, pm, f, B, cosets, ncosets, F, ws, st);
 }
 
 int snfft_inverse(const snfft_plan_t* p, const void* F, int64_t B, void* f, void* ws, size_t ws_bytes, void* stream) {

@@ -56,3 +56,100 @@ def sn_fft_batch_sharded(fn_vals: torch.Tensor, n: int, group=None, gather: bool
 def sn_ifft_batch_sharded(ft: dict, n: int) -> torch.Tensor:
     """Inverse of a local (per-rank) coefficient dict: no communication."""
     return sn_ifft(ft, n)
+
+
+# ---------------------------------------------------------------------------
+# One large function sharded over the top-level cosets (BASELINE config 5, SURVEY 8e)
+# ---------------------------------------------------------------------------
+def coset_shards(n: int, world_size: int):
+    """Top-level cosets {sigma : sigma[i] = n-1}, i in range(n), dealt to the ranks as contiguous
+    ranges whose sizes differ by at most one (rank r owns cosets [lo_r, hi_r))."""
+    return [shard_bounds(n, world_size, r) for r in range(world_size)]
+
+
+def partition_owners(dims, world_size: int):
+    """Which rank ends up with which partition after the reduce-scatter.
+
+    Greedy bin packing of the partitions by d^2 (largest first into the emptiest bin); returns
+    (owner[p] for every partition, bin_size) with bin_size = the largest bin: ncclReduceScatter wants
+    equal receive counts, so every rank's slot of the send buffer is padded to that size."""
+    order = sorted(range(len(dims)), key=lambda p: -dims[p] * dims[p])
+    load = [0] * world_size
+    owner = [0] * len(dims)
+    for p in order:
+        r = min(range(world_size), key=lambda q: (load[q], q))
+        owner[p] = r
+        load[r] += dims[p] * dims[p]
+    return owner, max(load) if load else 0
+
+
+def _reduce_scatter_sum(send: torch.Tensor, recv: torch.Tensor, group=None):
+    """recv <- sum over ranks of this rank's slot of `send` ([world][slot])."""
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(recv, send, op=dist.ReduceOp.SUM, group=group)
+    else:
+        # gloo (the CPU test-suite's transport) has no reduce_scatter: all_reduce, keep the own slot
+        dist.all_reduce(send, op=dist.ReduceOp.SUM, group=group)
+        recv.copy_(send.view(dist.get_world_size(group), -1)[dist.get_rank(group)])
+
+
+def sn_fft_coset_partial(fn_vals: torch.Tensor, n: int, cosets):
+    """The terms of the top-level Clausen sum (fourier.py:253-273) that `cosets` own, as a packed
+    coefficient tensor ((B * n!,), same layout as sn_fft's internal buffer) plus the plan."""
+    from . import _lib
+    from .fourier import _check_input, _device_ctx, _stream_ptr, _to_device
+    from .plan import get_plan
+    import ctypes
+    _check_input(fn_vals, n)
+    if n < 3:
+        raise ValueError("coset sharding needs n >= 3")
+    x, _ = _to_device(fn_vals)
+    f2d = x.reshape(-1, x.shape[-1]).contiguous()
+    batch = f2d.shape[0]
+    cosets = sorted(int(c) for c in cosets)
+    plan = get_plan(n, f2d.dtype, f2d.device)
+    sub = get_plan(n - 1, f2d.dtype, f2d.device)
+    packed = torch.empty(batch * plan.nfact, dtype=f2d.dtype, device=f2d.device)
+    if batch:
+        lib = _lib.load()
+        arr = (ctypes.c_int * max(len(cosets), 1))(*cosets)
+        with _device_ctx(f2d.device):
+            nbytes = lib.snfft_forward_cosets_workspace_bytes(plan.handle, sub.handle, batch, len(cosets))
+            ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=f2d.device)
+            _lib.check(lib.snfft_forward_cosets(plan.handle, sub.handle, f2d.data_ptr(), batch, arr, len(cosets),
+                                                packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(f2d.device)),
+                       "snfft_forward_cosets")
+    return plan, packed, batch
+
+
+def sn_fft_coset_sharded(fn_vals: torch.Tensor, n: int, group=None) -> dict:
+    """Forward transform of one large function (or a small batch) that every rank holds, sharded over the
+    top-level cosets: rank r transforms the restrictions of f to its cosets (S_{n-1} sub-transforms), applies
+    its terms of the level-n step, and one sum reduce-scatter over the packed coefficients leaves every rank
+    with a subset of the partitions.  Returns {partition: F(partition)} for the partitions THIS rank owns
+    (shapes as sn_fft); `partition_owners` tells which rank has which."""
+    if not dist.is_initialized():
+        raise RuntimeError("sn_fft_coset_sharded needs an initialised torch.distributed process group")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = coset_shards(n, world)[rank]
+    plan, packed, batch = sn_fft_coset_partial(fn_vals, n, range(lo, hi))
+    owner, bin_size = partition_owners(plan.dims, world)
+    # send buffer [world][bin_size * batch]: the partitions of bin r back to back, zero padded
+    send = torch.zeros(world * bin_size * batch, dtype=packed.dtype, device=packed.device)
+    slots, fill = {}, [0] * world
+    for p, (d, off) in enumerate(zip(plan.dims, plan.offsets)):
+        r = owner[p]
+        start = (r * bin_size + fill[r]) * batch
+        send[start:start + d * d * batch].copy_(packed[off * batch:(off + d * d) * batch])
+        slots[p] = fill[r]
+        fill[r] += d * d
+    recv = torch.empty(bin_size * batch, dtype=packed.dtype, device=packed.device)
+    _reduce_scatter_sum(send, recv, group)
+    lead = tuple(fn_vals.shape[:-1])
+    out = {}
+    for p, (lam, d) in enumerate(zip(plan.partitions, plan.dims)):
+        if owner[p] != rank:
+            continue
+        blk = recv[slots[p] * batch:(slots[p] + d * d) * batch]
+        out[lam] = blk.view(lead) if d == 1 else blk.view(lead + (d, d))
+    return out

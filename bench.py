@@ -30,6 +30,17 @@ sys.path.insert(0, ROOT)
 METRIC = "sn_fft_ifft_pairs_per_s"
 UNIT = "transforms/s"
 
+# Libraries (NCCL prints its version banner) write to file descriptor 1; the contract is ONE JSON line on
+# stdout, so fd 1 is pointed at stderr for the whole run and the line goes to a private copy of stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    with os.fdopen(os.dup(_REAL_STDOUT), "w") as fh:
+        fh.write(json.dumps(line) + "\n")
+        fh.flush()
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -41,6 +52,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=128, help="functions per GPU")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="batch", choices=["batch", "coset"],
+                    help="batch: BASELINE configs 2-4 (default); coset: config 5, ONE S_n function (default n = 11) sharded "
+                         "over the top-level cosets with a reduce-scatter by partition (torchrun, N >= 2)")
     return ap.parse_args()
 
 
@@ -153,7 +167,7 @@ def run_reference(a):
                          "sample": f"{sample} functions per step ({workers} processes x 1), forward+inverse"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -296,14 +310,95 @@ def run_native(a):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{nfunc} functions of the same workload, forward+inverse, "
                                               "oracle port (sparse YOR sweeps, C inner loops, 1 thread)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_coset(a):
+    """BASELINE config 5: forward transform of ONE function on S_n, sharded over the top-level cosets;
+    the ranks finish with an NCCL reduce-scatter by partition.  Strong scaling: the work is fixed."""
+    import torch
+    import torch.distributed as dist
+    from algebraist_b200 import sn_fft
+    from algebraist_b200.distributed import coset_shards, partition_owners, sn_fft_coset_sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev) if world > 1 else dist.init_process_group(
+        "nccl", init_method="tcp://127.0.0.1:29531", rank=0, world_size=1, device_id=dev)
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+    esize = 4 if a.dtype == "f32" else 8
+    n = a.n if a.n != 10 else 11
+    nf = math.factorial(n)
+    torch.manual_seed(5)                                  # every rank holds the same function
+    f = torch.randn(nf, dtype=tdt, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > L2, written between steps
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        mine = sn_fft_coset_sharded(f, n)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    times = []
+    for _ in range(a.steps):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mine = sn_fft_coset_sharded(f, n)
+        e1.record()
+        barrier()
+        times.append(e0.elapsed_time(e1))
+    t = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    clocks = sampler.summary()
+    # parity: the owned partitions against the single-GPU transform of the same function (rank 0 only: 3 x 160 MB)
+    err = 0.0
+    if rank == 0:
+        full = sn_fft(f, n)
+        for lam, v in mine.items():
+            err = max(err, ((v - full[lam]).double().norm() / full[lam].double().norm().clamp_min(1e-30)).item())
+    power = torch.zeros(1, dtype=torch.float64, device=dev)
+    for lam, v in mine.items():
+        power += v.double().pow(2).sum() * (1 if v.dim() == 0 else v.shape[-1]) / nf
+    dist.all_reduce(power)
+    plancherel = abs(power.item() / f.double().pow(2).sum().item() - 1.0)
+    if rank == 0:
+        from algebraist_b200.plan import get_plan
+        plan = get_plan(n, tdt, dev)
+        owner, bin_size = partition_owners(plan.dims, world)
+        line = {
+            "metric": "sn_fft_forward_per_s", "value": a.steps / (ms / 1000.0), "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": f"S{n} {a.dtype} forward FFT of one function, sharded over top-level cosets",
+                       "n": n, "parallelism": f"coset-shard x{world} + reduce-scatter by partition",
+                       "cosets_per_rank": [hi - lo for lo, hi in coset_shards(n, world)],
+                       "reduce_scatter_bytes_per_rank": bin_size * esize * (world - 1),
+                       "l2_policy": "256 MB flush buffer written between timed iterations",
+                       "rel_err_vs_single_gpu": err, "plancherel_rel_err": plancherel},
+            "clocks": clocks,
+        }
+        emit(line)
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "coset":
+        run_coset(args)
     else:
         run_native(args)

@@ -115,6 +115,26 @@ int snfft_inverse(const snfft_plan_t* plan, const void* F, int64_t B, void* f,
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Partial forward transform over a subset of the top-level cosets
+ * {sigma : sigma[i] = n-1} (the coset-sharded transform of one large function,
+ * SURVEY 8e / BASELINE config 5):
+ *   F_partial(lambda) = sum_{i in cosets} rho_lambda(c_i) . blockdiag_mu F^(i)_mu
+ * i.e. the terms of the top-level sum of fourier_projection (fourier.py:253-273)
+ * that the given cosets own; restrict_to_coset (fourier.py:63-80) and the
+ * S_{n-1} sub-transforms run inside.  The partial results of a partition of
+ * range(n) add up to snfft_forward's output (same packed layout), so a rank
+ * calls this with its cosets and the ranks finish with a sum reduction
+ * (ncclReduceScatter) -- no other exchange.  `cosets` is a HOST array of
+ * strictly ascending indices; plan_nm1 is the S_{n-1} plan of the same dtype
+ * and device.  ncosets == 0 writes zeros.
+ */
+size_t snfft_forward_cosets_workspace_bytes(const snfft_plan_t* plan_n, const snfft_plan_t* plan_nm1, int64_t B,
+                                            int ncosets);
+int snfft_forward_cosets(const snfft_plan_t* plan_n, const snfft_plan_t* plan_nm1, const void* f, int64_t B,
+                         const int* cosets, int ncosets, void* F, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/*
  * Same transforms with HOST buffers (pageable or pinned): copies in, runs the
  * device pipeline, copies out, and returns after the result is in `F_host` /
  * `f_host`.  Scratch is owned by the plan and grows on demand.

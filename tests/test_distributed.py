@@ -69,3 +69,66 @@ def test_batch_sharding_world2_gloo(tmp_path, n, batch):
         for lam, r in ref.items():
             v = got["_".join(map(str, lam))]
             assert np.allclose(v.reshape(r.shape), r, atol=1e-11), (rank, lam)
+
+
+def test_coset_shards_and_partition_owners():
+    from algebraist_b200.distributed import coset_shards, partition_owners
+    from oracle import sn_oracle as O
+    for n, world in ((11, 8), (11, 2), (12, 4), (5, 8)):
+        spans = coset_shards(n, world)
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    dims = [O.dim(lam) for lam in O.generate_partitions(9)]
+    for world in (1, 2, 4, 8):
+        owner, bin_size = partition_owners(dims, world)
+        loads = [sum(d * d for d, o in zip(dims, owner) if o == r) for r in range(world)]
+        assert sum(loads) == math.factorial(9) and max(loads) == bin_size
+        assert bin_size <= math.factorial(9) / world + max(dims) ** 2     # greedy: within one block of even
+
+
+def _coset_worker(rank, world, port, n, batch, emu_path, out_dir):
+    import ctypes
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from algebraist_b200 import _lib
+    from algebraist_b200.distributed import sn_fft_coset_sharded
+    from conftest import package_on_emu
+    emu = _lib.bind(ctypes.CDLL(emu_path))
+    torch.manual_seed(11)                                  # every rank holds the same function(s)
+    f = torch.randn(batch, math.factorial(n), dtype=torch.float64) if batch else torch.randn(math.factorial(n), dtype=torch.float64)
+    with package_on_emu(emu):
+        mine = sn_fft_coset_sharded(f, n)
+    np.savez(os.path.join(out_dir, f"coset_rank{rank}.npz"), **{"_".join(map(str, k)): v.numpy() for k, v in mine.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,batch", [(6, 0), (5, 2)])
+def test_coset_sharding_world2_gloo(tmp_path, n, batch):
+    """One function sharded over the top-level cosets: the partitions the two ranks end up with are
+    disjoint, cover everything, and equal the oracle's transform."""
+    from oracle import sn_oracle as O
+    from algebraist_b200.distributed import partition_owners
+    emu_path = build_emu()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_coset_worker, args=(2, port, n, batch, emu_path, str(tmp_path)), nprocs=2, join=True)
+    torch.manual_seed(11)
+    f = (torch.randn(batch, math.factorial(n), dtype=torch.float64) if batch
+         else torch.randn(math.factorial(n), dtype=torch.float64)).numpy()
+    ref = O.sn_fft_packed(f.reshape(-1, f.shape[-1]), n)
+    parts = list(O.generate_partitions(n))
+    owner, _ = partition_owners([O.dim(lam) for lam in parts], 2)
+    seen = set()
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), f"coset_rank{rank}.npz"))
+        for k in got.files:
+            lam = tuple(int(x) for x in k.split("_"))
+            assert owner[parts.index(lam)] == rank and lam not in seen
+            seen.add(lam)
+            assert np.allclose(got[k].reshape(ref[lam].shape), ref[lam], atol=1e-11), (rank, lam)
+    assert seen == set(parts)

@@ -244,3 +244,35 @@ def test_kernel_families_vs_oracle(A, mode, dt):
         lib.snfft_debug_tb_mode(-1)
         P._cache.clear()
         P._cache.update(saved)
+
+
+@pytest.mark.parametrize("n,dt", [(9, "f64"), (10, "f32"), (11, "f32")])
+def test_coset_partials_sum_to_full_transform(A, n, dt):
+    """snfft_forward_cosets (the per-rank work of the coset-sharded transform, BASELINE config 5): the partial
+    transforms of a partition of the top-level cosets add up to the full transform; n = 11 also checks
+    Plancherel on the 39.9M-entry function."""
+    from algebraist_b200.distributed import coset_shards, sn_fft_coset_partial
+    torch.manual_seed(n)
+    nf = math.factorial(n)
+    f = torch.randn(nf, dtype=TDT[dt], device="cuda")
+    full = A.sn_fft(f, n)
+    total = None
+    for lo, hi in coset_shards(n, 4):
+        plan, packed, batch = sn_fft_coset_partial(f, n, range(lo, hi))
+        total = packed.clone() if total is None else total + packed
+    for lam, d, off in zip(plan.partitions, plan.dims, plan.offsets):
+        got = total[off:off + d * d].reshape(full[lam].shape)
+        ref = full[lam]
+        assert ((got - ref).double().norm() / ref.double().norm()).item() < 10 * TOL[dt], lam
+    power = sum(v.double().pow(2).sum() * (1 if v.dim() == 0 else v.shape[-1]) / nf for v in full.values())
+    assert abs(power.item() / f.double().pow(2).sum().item() - 1) < 10 * TOL[dt]
+
+
+def test_vs_oracle_n11(A):
+    """One S_11 function (39.9M entries, BASELINE config 5's size) against the oracle, fp32."""
+    n = 11
+    rng = np.random.default_rng(11)
+    f = rng.standard_normal((1, math.factorial(n)))
+    ref = O.sn_fft_packed_c(f, n)
+    ft = A.sn_fft(torch.from_numpy(f[0]).float().cuda(), n)
+    _check_dict(ft, ref, TOL["f32"])
