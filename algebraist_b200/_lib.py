@@ -59,6 +59,7 @@ SIGNATURES = {
     "snfft_debug_force_class": (None, [c_int]),
     "snfft_debug_disable_base": (None, [c_int]),
     "snfft_debug_tb_mode": (None, [c_int]),
+    "snfft_debug_scalar_gather": (None, [c_int]),
 }
 
 

@@ -321,26 +321,37 @@ def gen_l6(forward):
     funcs, calls = [], []
     total = 0
     name = "l6_forward" if forward else "l6_inverse"
-    groups = partitions(k) if forward else partitions(k - 1)
+    groups = partitions(k - 1)
     for g, part in enumerate(groups):
         body = []
         if forward:
-            lam = part
-            for b in range(len(children(lam))):
-                for c in range(dim(children(lam)[b])):
-                    em = Emitter()
+            # child-major: the 6 * d_mu inputs of column c of F_mu are loaded once and shared by every
+            # parent lambda of mu (loading them per parent re-read each child 2.6 times from DRAM)
+            mu = part
+            for c in range(dim(mu)):
+                em = Emitter()
+                cache = {}
 
-                    def load(mu, r, cc, i, em=em):
-                        e5 = coef_off(mu) + r * dim(mu) + cc
-                        return em.tmp(f"in[(size_t){e5 * 6 + i} * s6]")
+                def load(m, r, cc, i, em=em, cache=cache):
+                    key = (m, r, cc, i)
+                    if key not in cache:
+                        e5 = coef_off(m) + r * dim(m) + cc
+                        cache[key] = em.tmp(f"in[(size_t){e5 * 6 + i} * s6]")
+                    return cache[key]
 
-                    def store(l, t, col, v, em=em):
-                        e6 = coef_off(l) + t * dim(l) + col
-                        em.lines.append(f"    out[(size_t){e6} * s6] = {value_expr(v)};")
+                def store(l, t, col, v, em=em):
+                    e6 = coef_off(l) + t * dim(l) + col
+                    em.lines.append(f"    out[(size_t){e6} * s6] = {value_expr(v)};")
 
-                    forward_column(em, k, lam, b, c, load, store)
-                    body.append("  {\n" + "\n".join(em.lines) + "\n  }\n  SNFFT_CODE_FENCE();")
-                    total += em.n
+                # issue every load of the column first (memory-level parallelism)
+                for r in range(dim(mu)):
+                    for i in range(k):
+                        load(mu, r, c, i)
+                for lam in partitions(k):
+                    if mu in children(lam):
+                        forward_column(em, k, lam, children(lam).index(mu), c, load, store)
+                body.append("  {\n" + "\n".join(em.lines) + "\n  }\n  SNFFT_CODE_FENCE();")
+                total += em.n
         else:
             mu = part
             for c in range(dim(mu)):

@@ -771,6 +771,111 @@ __global__ void __launch_bounds__(PK_T * 8) pack_kernel(const T* __restrict__ in
 }
 
 // ---------------------------------------------------------------------------
+// Vectorised pack / unpack (B % VT == 0): same register-block transposition as gather_vec_kernel.  A CTA
+// owns TR = 32 * VT consecutive coefficients e of one partition and walks over the batch.  The
+// instance-fastest side moves 16-byte vectors along b; the packed side moves 16-byte vectors along e when
+// d^2 is a multiple of VT and single elements otherwise (odd d).   grid (e-tiles of all partitions), 256 threads
+// ---------------------------------------------------------------------------
+template <typename T, bool TO_PACKED>
+__global__ void __launch_bounds__(256) pack_vec_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                       const long long* __restrict__ coef_off,
+                                                       const long long* __restrict__ tile_prefix, int nparts,
+                                                       long long batch) {
+    constexpr int VT = 16 / (int)sizeof(T), TB = 8 * VT, TR = 32 * VT;
+    using PV = Pack<T, VT>;
+    alignas(16) __shared__ T tile[TR * TB];
+    const int tid = threadIdx.x;
+    int lam = 0, hi = nparts - 1;
+    while (lam < hi) {
+        const int mid = (lam + hi + 1) / 2;
+        if (tile_prefix[mid] <= (long long)blockIdx.x) lam = mid;
+        else hi = mid - 1;
+    }
+    const long long lo = coef_off[lam], dd = coef_off[lam + 1] - lo;
+    const long long e0 = ((long long)blockIdx.x - tile_prefix[lam]) * TR;
+    const bool evec = dd % VT == 0;
+    const int cb = tid & 31, bq = tid >> 5;       // packed side: coefficients e0 + VT*cb .., batch rows VT*bq ..
+    const int ch = tid & 7, rq = tid >> 3;        // instance side: coefficient e0 + rq + 32*it, batch chunk ch
+    const T* __restrict__ pk_in = in + lo * batch;
+    T* __restrict__ pk_out = out + lo * batch;
+    for (long long b0 = 0; b0 < batch; b0 += TB) {
+        if (TO_PACKED) {
+#pragma unroll
+            for (int it = 0; it < VT; ++it) {
+                const int rr = rq + 32 * it;
+                const long long e = e0 + rr, b = b0 + VT * ch;
+                PV v;
+                if (e < dd && b < batch) v = *reinterpret_cast<const PV*>(in + (lo + e) * batch + b);
+                else {
+#pragma unroll
+                    for (int q = 0; q < VT; ++q) v.v[q] = T(0);
+                }
+                *reinterpret_cast<PV*>(tile + rr * TB + ((ch ^ ((rr / VT) & 7)) * VT)) = v;
+            }
+            __syncthreads();
+            PV col[VT];
+#pragma unroll
+            for (int j = 0; j < VT; ++j)
+                col[j] = *reinterpret_cast<const PV*>(tile + (VT * cb + j) * TB + ((bq ^ (cb & 7)) * VT));
+#pragma unroll
+            for (int i = 0; i < VT; ++i) {
+                const long long b = b0 + VT * bq + i, e = e0 + VT * cb;
+                if (b >= batch) continue;
+                T* __restrict__ dst = pk_out + b * dd + e;
+                if (evec) {
+                    if (e < dd) {
+                        PV row;
+#pragma unroll
+                        for (int j = 0; j < VT; ++j) row.v[j] = col[j].v[i];
+                        *reinterpret_cast<PV*>(dst) = row;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VT; ++j)
+                        if (e + j < dd) dst[j] = col[j].v[i];
+                }
+            }
+            __syncthreads();
+        } else {
+            PV blk[VT];
+#pragma unroll
+            for (int i = 0; i < VT; ++i) {
+                const long long b = b0 + VT * bq + i, e = e0 + VT * cb;
+                const T* __restrict__ src = pk_in + b * dd + e;
+#pragma unroll
+                for (int v = 0; v < VT; ++v) blk[i].v[v] = T(0);
+                if (b < batch) {
+                    if (evec) {
+                        if (e < dd) blk[i] = *reinterpret_cast<const PV*>(src);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < VT; ++j)
+                            if (e + j < dd) blk[i].v[j] = src[j];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VT; ++j) {
+                PV col;
+#pragma unroll
+                for (int i = 0; i < VT; ++i) col.v[i] = blk[i].v[j];
+                *reinterpret_cast<PV*>(tile + (VT * cb + j) * TB + ((bq ^ (cb & 7)) * VT)) = col;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < VT; ++it) {
+                const int rr = rq + 32 * it;
+                const long long e = e0 + rr, b = b0 + VT * ch;
+                if (e < dd && b < batch)
+                    *reinterpret_cast<PV*>(out + (lo + e) * batch + b) =
+                        *reinterpret_cast<const PV*>(tile + rr * TB + ((ch ^ ((rr / VT) & 7)) * VT));
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // input gather / output scatter: the composition of restrict_to_coset over all
 // levels (fourier.py:253) as one tiled transpose.  grid (ranks/64, B/32), 256 thr
 //   GATHER :  x1[p1(r) * B + b] = f[b * n! + r]
@@ -821,6 +926,95 @@ __global__ void __launch_bounds__(GS_THREADS) gather_kernel(const T* __restrict_
             const int bb = e / GS_TR, rr = e % GS_TR;
             if (b0 + bb < ia.batch && r0 + rr < ia.nfact)
                 out[(b0 + bb) * ia.nfact + r0 + rr] = tile[bb * (GS_TR + 1) + rr];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Vectorised gather / scatter (B % VT == 0, VT = 16 bytes / sizeof(T)): every global access is a 16-byte
+// vector, the transposition happens in VT x VT register blocks, and the shared tile [TR][TB] keeps rows of
+// TB = 8 * VT batch entries (eight 16-byte chunks, XOR-swizzled by the rank so that both sides are
+// conflict free).  A CTA owns TR = 32 * VT consecutive ranks and walks over the whole batch; p1tab (the
+// chain index of every rank, 32-bit, built once per plan) replaces the per-rank index computation.
+//   grid (ranks / TR), 256 threads
+// ---------------------------------------------------------------------------
+template <typename T, bool SCATTER>
+__global__ void __launch_bounds__(256) gather_vec_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                         const uint32_t* __restrict__ p1tab, const IndexArgs ia) {
+    constexpr int VT = 16 / (int)sizeof(T), TB = 8 * VT, TR = 32 * VT;
+    using PV = Pack<T, VT>;
+    alignas(16) __shared__ T tile[TR * TB];
+    const int tid = threadIdx.x;
+    const long long r0 = (long long)blockIdx.x * TR;
+    // function side (f[b][r]): thread (cb, bq) owns ranks r0 + VT*cb .. and batch rows VT*bq ..
+    const int cb = tid & 31, bq = tid >> 5;
+    // level side (x1[p1(r)][b]): thread (rq, ch) owns rank rq + 32*it and the 16-byte batch chunk ch
+    const int ch = tid & 7, rq = tid >> 3;
+    const bool f_ok = r0 + (long long)VT * cb < ia.nfact;       // n! is a multiple of VT for n >= 4
+    long long p1[VT];
+#pragma unroll
+    for (int it = 0; it < VT; ++it) {
+        const long long r = r0 + rq + 32 * it;
+        p1[it] = r < ia.nfact ? (p1tab ? (long long)p1tab[r] : chain_index(ia.n, r, ia.fact)) : -1;
+    }
+    for (long long b0 = 0; b0 < ia.batch; b0 += TB) {
+        if (!SCATTER) {
+            PV blk[VT];                                          // blk[i] = f[b0 + VT*bq + i][r0 + VT*cb ..]
+#pragma unroll
+            for (int i = 0; i < VT; ++i) {
+                const long long b = b0 + VT * bq + i;
+                if (f_ok && b < ia.batch) blk[i] = *reinterpret_cast<const PV*>(in + b * ia.nfact + r0 + VT * cb);
+                else {
+#pragma unroll
+                    for (int v = 0; v < VT; ++v) blk[i].v[v] = T(0);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VT; ++j) {                       // rank VT*cb + j, batch chunk bq
+                PV col;
+#pragma unroll
+                for (int i = 0; i < VT; ++i) col.v[i] = blk[i].v[j];
+                *reinterpret_cast<PV*>(tile + (VT * cb + j) * TB + ((bq ^ (cb & 7)) * VT)) = col;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < VT; ++it) {
+                const int rr = rq + 32 * it;
+                const long long b = b0 + VT * ch;
+                if (p1[it] >= 0 && b < ia.batch)
+                    *reinterpret_cast<PV*>(out + p1[it] * ia.batch + b) =
+                        *reinterpret_cast<const PV*>(tile + rr * TB + ((ch ^ ((rr / VT) & 7)) * VT));
+            }
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int it = 0; it < VT; ++it) {
+                const int rr = rq + 32 * it;
+                const long long b = b0 + VT * ch;
+                PV v;
+                if (p1[it] >= 0 && b < ia.batch) v = *reinterpret_cast<const PV*>(in + p1[it] * ia.batch + b);
+                else {
+#pragma unroll
+                    for (int q = 0; q < VT; ++q) v.v[q] = T(0);
+                }
+                *reinterpret_cast<PV*>(tile + rr * TB + ((ch ^ ((rr / VT) & 7)) * VT)) = v;
+            }
+            __syncthreads();
+            PV col[VT];
+#pragma unroll
+            for (int j = 0; j < VT; ++j)
+                col[j] = *reinterpret_cast<const PV*>(tile + (VT * cb + j) * TB + ((bq ^ (cb & 7)) * VT));
+#pragma unroll
+            for (int i = 0; i < VT; ++i) {
+                const long long b = b0 + VT * bq + i;
+                if (f_ok && b < ia.batch) {
+                    PV row;
+#pragma unroll
+                    for (int j = 0; j < VT; ++j) row.v[j] = col[j].v[i];
+                    *reinterpret_cast<PV*>(out + b * ia.nfact + r0 + VT * cb) = row;
+                }
+            }
+            __syncthreads();
         }
     }
 }
@@ -893,6 +1087,12 @@ __global__ void restrict_kernel(const T* __restrict__ f, T* __restrict__ out, co
         src += lj * ra.ia.fact[n - 1 - pos];
     }
     out[e] = f[b * ra.ia.nfact + src];
+}
+
+__global__ void chain_index32_kernel(uint32_t* __restrict__ p1, const IndexArgs ia) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ia.nfact) return;
+    p1[r] = (uint32_t)chain_index(ia.n, r, ia.fact);
 }
 
 __global__ void chain_index_kernel(long long* __restrict__ p1, const IndexArgs ia) {

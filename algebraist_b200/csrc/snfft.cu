@@ -64,6 +64,7 @@ static const int kNumClasses = 6;
 
 static std::atomic<int> g_force_class{-1};
 static std::atomic<int> g_no_base{0};
+static std::atomic<int> g_no_vec_gather{0};   // test hook: 1 = always the scalar gather / scatter kernel
 static std::atomic<int> g_tb_mode{-1};      // -1 automatic, 0 sweep-per-pass kernels only, 1..3 force s fused top sweeps
 static std::atomic<long long> g_launches{0};
 static thread_local std::string g_error;
@@ -133,9 +134,12 @@ struct snfft_plan {
     std::vector<DevLevel> lev;      // lev[k], k = 2..n
     std::vector<void*> allocs;      // every device allocation of the tables
     IndexArgs ia;
+    void* d_p1 = nullptr;               // chain index of every rank (uint32), n <= 11; larger n compute it per tile
     void* d_coef_off = nullptr;         // device copy of the level-n coefficient offsets (pack / unpack)
     void* d_tile_prefix = nullptr;      // first 32-coefficient tile of every partition (pack / unpack grid)
     long long n_pack_tiles = 0;
+    void *d_vtile_prefix32 = nullptr, *d_vtile_prefix64 = nullptr;   // the same for pack_vec_kernel (128 / 64 coefficients)
+    long long n_vtiles32 = 0, n_vtiles64 = 0;
     // per-row YOR tables of level n for snfft_dense_rep, uploaded on first use
     void *rt_partner = nullptr, *rt_diag = nullptr, *rt_off = nullptr;
     std::vector<long long> rt_base;     // per partition: offset of its [n-1][d] block
@@ -515,6 +519,16 @@ template <typename T, bool SCATTER>
 static int run_gather(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
     IndexArgs ia = p->ia;
     ia.batch = B;
+    constexpr int VT = 16 / (int)sizeof(T);
+    if (p->n >= 4 && B % VT == 0 && (uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0 && g_no_vec_gather.load() == 0) {
+        dim3 grid((unsigned)((ia.nfact + 32 * VT - 1) / (32 * VT)), 1, 1), block(256, 1, 1);
+        ProfScope prof(p, st, SCATTER ? 3 : 2, 1, -2, ia.nfact);
+        auto kfn = gather_vec_kernel<T, SCATTER>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)in, (T*)out, (const uint32_t*)p->d_p1, ia);
+        g_launches.fetch_add(1);
+        SNFFT_CUDA(cudaGetLastError());
+        return SNFFT_OK;
+    }
     dim3 grid((unsigned)((ia.nfact + GS_TR - 1) / GS_TR), (unsigned)((B + GS_TB - 1) / GS_TB), 1);
     dim3 block(GS_THREADS, 1, 1);
     ProfScope prof(p, st, SCATTER ? 3 : 2, 1, -1, ia.nfact);
@@ -572,6 +586,19 @@ static int run_base(const snfft_plan* p, const void* in, void* out, long long B,
 template <typename T, bool TO_PACKED>
 static int run_pack(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
     const HostLevel& L = p->host.levels[p->n];
+    constexpr int VT = 16 / (int)sizeof(T);
+    if (B % VT == 0 && (uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0 && g_no_vec_gather.load() == 0) {
+        const void* prefix = sizeof(T) == 4 ? p->d_vtile_prefix32 : p->d_vtile_prefix64;
+        const long long vt = sizeof(T) == 4 ? p->n_vtiles32 : p->n_vtiles64;
+        dim3 grid((unsigned)vt, 1, 1), block(256, 1, 1);
+        ProfScope prof(p, st, TO_PACKED ? 6 : 7, p->n, -2, p->host.factorial[p->n]);
+        auto kfn = pack_vec_kernel<T, TO_PACKED>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)in, (T*)out, (const long long*)p->d_coef_off,
+                     (const long long*)prefix, (int)L.shapes.size(), B);
+        g_launches.fetch_add(1);
+        SNFFT_CUDA(cudaGetLastError());
+        return SNFFT_OK;
+    }
     const long long tiles = p->n_pack_tiles * ((B + PK_T - 1) / PK_T);
     dim3 grid((unsigned)tiles, 1, 1), block(PK_T * 8, 1, 1);
     ProfScope prof(p, st, TO_PACKED ? 6 : 7, p->n, -1, p->host.factorial[p->n]);
@@ -798,6 +825,7 @@ void snfft_debug_force_class(int cls) { g_force_class.store(cls); }
 // table-driven kernels, 2 = table-driven shared-memory base kernel
 void snfft_debug_disable_base(int mode) { g_no_base.store(mode); }
 void snfft_debug_tb_mode(int mode) { g_tb_mode.store(mode); }
+void snfft_debug_scalar_gather(int on) { g_no_vec_gather.store(on); }
 
 int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
     if (!out) return set_error(SNFFT_EINVAL, "out is NULL");
@@ -827,6 +855,26 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
             p->n_pack_tiles = t;
             int rc = upload(p, offs, &p->d_coef_off);
             if (!rc) rc = upload(p, pre, &p->d_tile_prefix);
+            for (int tr : {128, 64}) {
+                std::vector<long long> vpre;
+                long long vt = 0;
+                for (const HostShape& S : L.shapes) {
+                    vpre.push_back(vt);
+                    vt += ((long long)S.dim * S.dim + tr - 1) / tr;
+                }
+                if (!rc) rc = upload(p, vpre, tr == 128 ? &p->d_vtile_prefix32 : &p->d_vtile_prefix64);
+                (tr == 128 ? p->n_vtiles32 : p->n_vtiles64) = vt;
+            }
+            if (!rc && n >= 4 && n <= 11) {       // 4 * n! bytes: 160 MB at n = 11
+                void* d = nullptr;
+                if (cudaMalloc(&d, (size_t)p->ia.nfact * sizeof(uint32_t)) == cudaSuccess) {
+                    p->allocs.push_back(d);
+                    p->d_p1 = d;
+                    dim3 grid((unsigned)((p->ia.nfact + 255) / 256), 1, 1), block(256, 1, 1);
+                    SNFFT_LAUNCH(chain_index32_kernel, grid, block, 0, (cudaStream_t)0, (uint32_t*)d, p->ia);
+                    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) rc = SNFFT_ECUDA;
+                }                                  // allocation failure: the kernels fall back to computing the index
+            }
             if (rc) {
                 snfft_plan_destroy(p);
                 return rc;

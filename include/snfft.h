@@ -210,6 +210,10 @@ void snfft_debug_disable_base(int mode);
  * created afterwards; both families must agree with the oracle. */
 void snfft_debug_tb_mode(int mode);
 
+/* Test hook: 1 = the input gather / output scatter always run the scalar tile kernel (the one used for
+ * batches that are not a multiple of 16 bytes), 0 = vectorised kernel when the batch allows (default). */
+void snfft_debug_scalar_gather(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -210,3 +210,28 @@ def test_tb_and_sweep_kernels_agree_ragged_batch(emu):
         finally:
             emu.snfft_plan_destroy(plan)
     assert rel_err(outs[1], outs[0]) < 1e-13 and rel_err(outs[2], outs[0]) < 1e-13
+
+
+@pytest.mark.parametrize("n,B,dt", [(4, 4, "f32"), (6, 8, "f32"), (7, 36, "f32"), (5, 2, "f64"), (6, 18, "f64")])
+def test_vector_gather_scatter(emu, n, B, dt):
+    """Batches that are a multiple of 16 bytes take the vectorised gather / scatter (register-block
+    transposes, cached chain-index table); it must agree bit for bit with the scalar tile kernel."""
+    rng = np.random.default_rng(n * 100 + B)
+    f = rng.standard_normal((B, math.factorial(n))).astype(DT[dt])
+    abi = CAbi(emu)
+    plan = abi.plan(n, DT[dt])
+    try:
+        packed = abi.forward(plan, f)
+        back = abi.inverse(plan, packed, B)
+        emu.snfft_debug_scalar_gather(1)
+        packed_s = abi.forward(plan, f)
+        back_s = abi.inverse(plan, packed, B)
+        assert np.array_equal(packed, packed_s) and np.array_equal(back, back_s)
+        ref = O.sn_fft_packed(f.astype(np.float64), n)
+        ft = unpack(packed, n, B)
+        for lam in ref:
+            assert rel_err(ft[lam], ref[lam]) < TOL[dt], lam
+        assert rel_err(back, f) < TOL[dt]
+    finally:
+        emu.snfft_debug_scalar_gather(0)
+        emu.snfft_plan_destroy(plan)
