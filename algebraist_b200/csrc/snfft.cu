@@ -15,6 +15,12 @@
         __pipeline_commit();       \
         __pipeline_wait_prior(0);  \
     } while (0)
+#define SNFFT_CP_ASYNC_COMMIT() __pipeline_commit()
+#define SNFFT_CP_ASYNC_WAIT_PRIOR(n) __pipeline_wait_prior(n)
+// named barriers of warp-specialised kernels: `count` threads (a multiple of 32) arrive or wait
+#define SNFFT_BAR_SYNC(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
+#define SNFFT_BAR_ARRIVE(id, count) asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory")
+#define SNFFT_FENCE_BLOCK() __threadfence_block()
 #define SNFFT_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
@@ -98,7 +104,7 @@ struct TaskRange {
 };
 
 struct TbRange {          // one launch of the TB kernels: tasks that share a tile width
-    int tcl, nt, begin, count, max_dmu, max_dlam, max_tt, max_ct, max_bt;
+    int tcl, nt, begin, count, max_dmu, max_dlam, max_tt, max_ct, max_bt, max_nsb;
     long long elems;
 };
 

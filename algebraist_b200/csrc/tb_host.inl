@@ -309,6 +309,7 @@ static int build_tb_level(snfft_plan* p, int k, int s) {
             r.max_tt = std::max(r.max_tt, t.tt_words);
             r.max_ct = std::max(r.max_ct, t.ct_len);
             r.max_bt = std::max(r.max_bt, t.bt_words);
+            r.max_nsb = std::max(r.max_nsb, t.nsb);
             tasks.push_back(t);
         }
         D.tb_franges.push_back(r);

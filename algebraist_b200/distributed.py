@@ -134,15 +134,20 @@ def sn_fft_coset_sharded(fn_vals: torch.Tensor, n: int, group=None) -> dict:
     lo, hi = coset_shards(n, world)[rank]
     plan, packed, batch = sn_fft_coset_partial(fn_vals, n, range(lo, hi))
     owner, bin_size = partition_owners(plan.dims, world)
-    # send buffer [world][bin_size * batch]: the partitions of bin r back to back, zero padded
-    send = torch.zeros(world * bin_size * batch, dtype=packed.dtype, device=packed.device)
-    slots, fill = {}, [0] * world
+    # send buffer [world][bin_size * batch]: the partitions of bin r back to back, zero padded (one batched copy)
+    pieces, slots, fill = [[] for _ in range(world)], {}, [0] * world
     for p, (d, off) in enumerate(zip(plan.dims, plan.offsets)):
         r = owner[p]
-        start = (r * bin_size + fill[r]) * batch
-        send[start:start + d * d * batch].copy_(packed[off * batch:(off + d * d) * batch])
+        pieces[r].append(packed[off * batch:(off + d * d) * batch])
         slots[p] = fill[r]
         fill[r] += d * d
+    pad = torch.zeros(max(bin_size - min(fill), 0) * batch, dtype=packed.dtype, device=packed.device)
+    flat = []
+    for r in range(world):
+        flat += pieces[r]
+        if fill[r] < bin_size:
+            flat.append(pad[:(bin_size - fill[r]) * batch])
+    send = torch.cat(flat)
     recv = torch.empty(bin_size * batch, dtype=packed.dtype, device=packed.device)
     _reduce_scatter_sum(send, recv, group)
     lead = tuple(fn_vals.shape[:-1])

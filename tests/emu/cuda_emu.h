@@ -74,6 +74,34 @@ inline void trampoline() {
 
 inline void yield_barrier() { swapcontext(&g.ctx[g.cur], &g.main_ctx); }
 
+// named barriers (bar.sync / bar.arrive id, count): a waiting fiber yields until the barrier's generation
+// changes.  Kernels that use them must not rely on the one-yield __syncthreads afterwards.
+struct NamedBar {
+    int arrived = 0;
+    unsigned gen = 0;
+};
+inline NamedBar named[16];
+inline void named_reset() {
+    for (NamedBar& b : named) b = NamedBar();
+}
+inline void named_arrive(int id, int count) {
+    NamedBar& b = named[id];
+    if (++b.arrived == count) {
+        b.arrived = 0;
+        ++b.gen;
+    }
+}
+inline void named_sync(int id, int count) {
+    NamedBar& b = named[id];
+    const unsigned my = b.gen;
+    if (++b.arrived == count) {
+        b.arrived = 0;
+        ++b.gen;
+        return;
+    }
+    while (b.gen == my) yield_barrier();
+}
+
 inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
     const int nt = (int)(block.x * block.y * block.z);
     std::vector<unsigned char> shared(smem + 64);
@@ -90,6 +118,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 blockIdx = dim3(bx, by, bz);
+                named_reset();
                 for (int t = 0; t < nt; ++t) {
                     getcontext(&g.ctx[t]);
                     g.ctx[t].uc_stack.ss_sp = g.stacks.data() + (size_t)t * Sched::kStack;
@@ -120,6 +149,11 @@ inline void __syncthreads() { emu::yield_barrier(); }
 
 #define SNFFT_CP_ASYNC(dst, src, bytes) std::memcpy(dst, src, bytes)
 #define SNFFT_CP_ASYNC_WAIT() ((void)0)
+#define SNFFT_CP_ASYNC_COMMIT() ((void)0)
+#define SNFFT_CP_ASYNC_WAIT_PRIOR(n) ((void)0)
+#define SNFFT_BAR_SYNC(id, count) emu::named_sync(id, count)
+#define SNFFT_BAR_ARRIVE(id, count) emu::named_arrive(id, count)
+#define SNFFT_FENCE_BLOCK() ((void)0)
 #define SNFFT_DYN_SMEM(name) unsigned char* name = emu::dyn_smem
 #define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) \
     emu::launch(grid, block, smem, [&]() { kfn(__VA_ARGS__); })
