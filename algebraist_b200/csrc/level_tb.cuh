@@ -279,8 +279,11 @@ __global__ void __launch_bounds__(NT, MINB) fwd_tb_kernel(const TbArgs<T> a) {
     const int tcl = a.tc_log2, TC = 1 << tcl, tcvl = tcl - VTL, TCV = 1 << tcvl;
     const long long ninst = a.ninst, ninst_prev = ninst * k;
     const long long qn = (long long)tk.d_mu * ninst;
-    const long long q0 = (long long)blockIdx.x << tcl;
-    if (q0 >= qn) return;
+    const long long ntiles = (qn + TC - 1) >> tcl;
+    // persistent over the tiles of this task: tile = blockIdx.x, blockIdx.x + gridDim.x, ...  The tables are
+    // staged once and the first inputs of the next tile are prefetched behind the last B phase of this one.
+    long long tile = blockIdx.x;
+    if (tile >= ntiles) return;
     const int bstride = a.bstride, xstride = a.xstride;
     T* __restrict__ work = reinterpret_cast<T*>(smem_raw);
     T* __restrict__ xin = work + (size_t)NBUF * bstride;
@@ -291,80 +294,92 @@ __global__ void __launch_bounds__(NT, MINB) fwd_tb_kernel(const TbArgs<T> a) {
     const long long rstride = (long long)tk.d_mu * ninst_prev;      // one row of F_mu
     const T* __restrict__ src0 = a.in + tk.mu_off * ninst_prev;     // element (row r, column c, coset i, inst) at
                                                                     // src0 + r * rstride + c * ninst_prev + i * ninst + inst
-    TbXfer<T> xf = tb_xfer<T>(q0, qn, ninst, ninst_prev, tcl, vec, tid, NT);
+    TbXfer<T> xf = tb_xfer<T>(tile << tcl, qn, ninst, ninst_prev, tcl, vec, tid, NT);
     tb_xfer_rows(xf, rstride, tcl);
     tb_stage_async(a, tk, ct, tt, bt, tid, NT);
-    {
-        const int nb0 = k < NBUF ? k : NBUF;
-        for (int m = 0; m < nb0; ++m)
-            tb_fill_async(xin + (size_t)m * xstride, src0 + (long long)m * ninst, tk.d_mu, xf, vec);
-    }
+    const int nb0 = k < NBUF ? k : NBUF;
+    for (int m = 0; m < nb0; ++m)
+        tb_fill_async(xin + (size_t)m * xstride, src0 + (long long)m * ninst, tk.d_mu, xf, vec);
 
     // B role: sub-block sb of column-instance slot bslot
     const int sb = tid >> tcl, bslot = tid & (TC - 1);
-    const long long bq = q0 + bslot;
-    const bool b_valid = sb < tk.nsb && bq < qn;
-    int bbase = 0, btype = 0;
-    T acc[MAXD];
-#pragma unroll
-    for (int r = 0; r < MAXD; ++r) acc[r] = T(0);
-
     int par = 0;                      // staging buffer of the current group
-    for (int i0 = 0; i0 < k; i0 += NBUF, par ^= 1) {
-        const int nb = (k - i0 < NBUF) ? (k - i0) : NBUF;
-        SNFFT_CP_ASYNC_WAIT();
-        __syncthreads();              // inputs of this group (and the tables) have landed; the previous group is done
-        if (i0 + NBUF < k && !(a.skip & 4)) {          // prefetch the next group's inputs behind this group's T and B phases
-            const int nbn = (k - i0 - NBUF < NBUF) ? (k - i0 - NBUF) : NBUF;
-            for (int m = 0; m < nbn; ++m)
-                tb_fill_async(xin + (size_t)((par ^ 1) * NBUF + m) * xstride, src0 + (long long)(i0 + NBUF + m) * ninst,
-                              tk.d_mu, xf, vec);
-        }
-        // ---- T phase: work[m] <- C_cls . (rows of F^(i0+m)_mu[:, c]) on the support of class cls
-        const int R = (int)tt[1];
-        const int rt = (a.skip & 1) ? 0 : (R << tcvl);
-        for (int item = tid; item < nb * rt; item += NT) {
-            int it = item, m = 0;
-            while (it >= rt) {
-                it -= rt;
-                ++m;
+    for (;;) {
+        const long long q0 = tile << tcl;
+        const long long bq = q0 + bslot;
+        const bool b_valid = sb < tk.nsb && bq < qn;
+        const long long tile_next = tile + gridDim.x;
+        int bbase = 0, btype = 0;
+        T acc[MAXD];
+#pragma unroll
+        for (int r = 0; r < MAXD; ++r) acc[r] = T(0);
+
+        for (int i0 = 0; i0 < k; i0 += NBUF, par ^= 1) {
+            const int nb = (k - i0 < NBUF) ? (k - i0) : NBUF;
+            SNFFT_CP_ASYNC_WAIT();
+            __syncthreads();          // inputs of this group (and the tables) have landed; the previous group is done
+            // prefetch the next group's inputs (of this tile, or the first group of the next tile) behind this
+            // group's T and B phases
+            if (i0 + NBUF < k) {
+                const int nbn = (k - i0 - NBUF < NBUF) ? (k - i0 - NBUF) : NBUF;
+                for (int m = 0; m < nbn; ++m)
+                    tb_fill_async(xin + (size_t)((par ^ 1) * NBUF + m) * xstride, src0 + (long long)(i0 + NBUF + m) * ninst,
+                                  tk.d_mu, xf, vec);
+            } else if (tile_next < ntiles) {
+                xf = tb_xfer<T>(tile_next << tcl, qn, ninst, ninst_prev, tcl, vec, tid, NT);
+                tb_xfer_rows(xf, rstride, tcl);
+                for (int m = 0; m < nb0; ++m)
+                    tb_fill_async(xin + (size_t)((par ^ 1) * NBUF + m) * xstride, src0 + (long long)m * ninst, tk.d_mu, xf,
+                                  vec);
             }
-            const int i = i0 + m;
-            const int cls = (k - 1 - i < s) ? (k - 1 - i) : s;
-            const int svo = (it & (TCV - 1)) * VT;
-            tb_t_item<T, MAXIN>(tt, ct, xin + (size_t)(par * NBUF + m) * xstride + svo, work + (size_t)m * bstride + svo,
-                                it >> tcvl, cls, tcl);
-        }
-        __syncthreads();              // work buffers complete
-        // ---- B phase: bottom sweeps of every chain of the group in registers, summed into acc
-        if (b_valid) {
-            const uint32_t bw0 = bt[sb * TB_BT_STRIDE];
-            bbase = (int)(bw0 & 0xffffu);
-            btype = (int)(bw0 >> 16);
-#pragma unroll 1
-            for (int m = 0; m < ((a.skip & 2) ? 0 : nb); ++m) {
+            // ---- T phase: work[m] <- C_cls . (rows of F^(i0+m)_mu[:, c]) on the support of class cls
+            const int R = (int)tt[1];
+            const int rt = (a.skip & 1) ? 0 : (R << tcvl);
+            for (int item = tid; item < nb * rt; item += NT) {
+                int it = item, m = 0;
+                while (it >= rt) {
+                    it -= rt;
+                    ++m;
+                }
                 const int i = i0 + m;
                 const int cls = (k - 1 - i < s) ? (k - 1 - i) : s;
-                TbFwdIO<T> io;
-                io.lo = bt[sb * TB_BT_STRIDE + 1 + 2 * cls];
-                io.hi = bt[sb * TB_BT_STRIDE + 2 + 2 * cls];
-                if ((io.lo | io.hi) == 0u) continue;
-                io.p = work + (size_t)m * bstride + ((size_t)bbase << tcl) + bslot;
-                io.stride = TC;
-                io.acc = acc;
-                bot_apply<T, MB, false>(btype, i, io);
+                const int svo = (it & (TCV - 1)) * VT;
+                tb_t_item<T, MAXIN>(tt, ct, xin + (size_t)(par * NBUF + m) * xstride + svo, work + (size_t)m * bstride + svo,
+                                    it >> tcvl, cls, tcl);
+            }
+            __syncthreads();          // work buffers complete
+            // ---- B phase: bottom sweeps of every chain of the group in registers, summed into acc
+            if (b_valid) {
+                const uint32_t bw0 = bt[sb * TB_BT_STRIDE];
+                bbase = (int)(bw0 & 0xffffu);
+                btype = (int)(bw0 >> 16);
+#pragma unroll 1
+                for (int m = 0; m < ((a.skip & 2) ? 0 : nb); ++m) {
+                    const int i = i0 + m;
+                    const int cls = (k - 1 - i < s) ? (k - 1 - i) : s;
+                    TbFwdIO<T> io;
+                    io.lo = bt[sb * TB_BT_STRIDE + 1 + 2 * cls];
+                    io.hi = bt[sb * TB_BT_STRIDE + 2 + 2 * cls];
+                    if ((io.lo | io.hi) == 0u) continue;
+                    io.p = work + (size_t)m * bstride + ((size_t)bbase << tcl) + bslot;
+                    io.stride = TC;
+                    io.acc = acc;
+                    bot_apply<T, MB, false>(btype, i, io);
+                }
             }
         }
-    }
 
-    if (b_valid) {
-        const long long c = bq / ninst, inst = bq - c * ninst;
-        T* __restrict__ dst = a.out + (tk.lam_off + (long long)bbase * tk.d_lam + tk.boff + c) * ninst + inst;
-        const long long ostride = (long long)tk.d_lam * ninst;
-        const int D = bot_dim<MB>(btype);
+        if (b_valid) {
+            const long long c = bq / ninst, inst = bq - c * ninst;
+            T* __restrict__ dst = a.out + (tk.lam_off + (long long)bbase * tk.d_lam + tk.boff + c) * ninst + inst;
+            const long long ostride = (long long)tk.d_lam * ninst;
+            const int D = bot_dim<MB>(btype);
 #pragma unroll
-        for (int r = 0; r < MAXD; ++r)
-            if (r < D) dst[r * ostride] = acc[r];
+            for (int r = 0; r < MAXD; ++r)
+                if (r < D) dst[r * ostride] = acc[r];
+        }
+        tile = tile_next;
+        if (tile >= ntiles) break;
     }
 }
 

@@ -111,6 +111,7 @@ struct TbRange {          // one launch of the TB kernels: tasks that share a ti
 struct DevLevel {
     // TB kernels (level_tb.cuh): tb_s = 0 means the level runs the sweep-per-pass kernels
     int tb_s = 0;
+    int tb_inv_nbuf = 2;                      // chains per pass of the inverse TB kernel at this level
     bool tb_fwd = false, tb_inv = false;      // which directions use them (the other runs the sweep kernels)
     void *tb_tasks = nullptr, *tb_itasks = nullptr, *tb_tt = nullptr, *tb_ct = nullptr, *tb_bt = nullptr;
     std::vector<TbRange> tb_franges, tb_iranges;

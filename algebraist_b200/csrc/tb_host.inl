@@ -12,6 +12,14 @@
 #endif
 
 constexpr int TB_NBUF = 2;          // chains per pass
+constexpr int TB_NBUF_ALL = 8;      // inverse steps with s = 1 (k <= 8): every chain in one pass, one CTA per tile
+// chains per pass of the inverse kernel at level k: with one fused top sweep the accumulators of all the
+// chains fit in registers (k <= 8 vectors), so one CTA handles a whole tile and every parent tile is read once
+static int tb_inv_nbuf(int k, int s) {
+    const char* e = std::getenv("SNFFT_TB_INV_ALL");       // tuning switch: 0 = always TB_NBUF chains per pass
+    if (e && e[0] == '0') return TB_NBUF;
+    return (s == 1 && k <= TB_NBUF_ALL) ? TB_NBUF_ALL : TB_NBUF;
+}
 // CTA shapes: fp32 runs 512 threads (one CTA per SM, <= 128 registers) when the sub-blocks of a tile need
 // them and 256 threads otherwise (two CTAs per SM); fp64 needs twice the registers and always runs 256.
 constexpr size_t TB_SMEM_CAP_1 = 200 * 1024, TB_SMEM_CAP_2 = 110 * 1024;
@@ -341,7 +349,7 @@ static int build_tb_level(snfft_plan* p, int k, int s) {
         int tcl = 7, nt = 0;
         for (; tcl >= vtl; --tcl) {
             nt = tb_pick_nt<T>(std::max((long long)maxnsb << tcl, (long long)it.R << (tcl - vtl)));
-            if (nt && tb_smem_bytes<T>(true, TB_NBUF, maxd << tcl, 0, mct, mtt, mbt) <= tb_smem_cap<T>(nt)) break;
+            if (nt && tb_smem_bytes<T>(true, tb_inv_nbuf(k, s), maxd << tcl, 0, mct, mtt, mbt) <= tb_smem_cap<T>(nt)) break;
         }
         if (tcl < vtl) return SNFFT_ENOTSUP;
         itasks_all.push_back(it);
@@ -378,6 +386,7 @@ static int build_tb_level(snfft_plan* p, int k, int s) {
     if ((rc = upload(p, ct, &D.tb_ct))) return rc;
     if ((rc = upload(p, bt, &D.tb_bt))) return rc;
     D.tb_s = s;
+    D.tb_inv_nbuf = tb_inv_nbuf(k, s);
     return SNFFT_OK;
 }
 
@@ -418,10 +427,20 @@ static int run_tb_level(const snfft_plan* p, int k, const void* in, void* out, l
         TbArgs<T> a = tb_args<T>(p, k, in, out, B, r);
         if (INVERSE) a.itasks += r.begin;
         else a.tasks += r.begin;
-        const size_t smem = tb_smem_bytes<T>(INVERSE, TB_NBUF, a.bstride, a.xstride, a.ct_smem_len, a.tt_smem_words,
+        const int nbuf = INVERSE ? D.tb_inv_nbuf : TB_NBUF;
+        const size_t smem = tb_smem_bytes<T>(INVERSE, nbuf, a.bstride, a.xstride, a.ct_smem_len, a.tt_smem_words,
                                              a.bt_smem_words);
         const long long tiles = (((long long)r.max_dmu * a.ninst) + (1ll << r.tcl) - 1) >> r.tcl;
-        const long long gx = INVERSE ? tiles * ((k + TB_NBUF - 1) / TB_NBUF) : tiles;
+        // forward: persistent CTAs, about SNFFT_TB_WAVES (default 8) CTAs per SM slot in flight over the whole range
+        long long gx = tiles * ((k + nbuf - 1) / nbuf);
+        if (!INVERSE) {
+            const char* e = std::getenv("SNFFT_TB_WAVES");
+            const long long waves = e ? std::atoll(e) : 8;
+            const long long slots = 148ll * (r.nt == 256 ? 2 : 1) * std::max(1ll, waves);
+            gx = waves <= 0 ? tiles : std::max(1ll, std::min(tiles, (slots + r.count - 1) / r.count));
+            const char* cap = std::getenv("SNFFT_TB_GX");      // test hook: explicit cap of the tile dimension
+            if (cap && std::atoll(cap) > 0) gx = std::min(gx, (long long)std::atoll(cap));
+        }
         if (gx > 0x7fffffffll) return set_error(SNFFT_ENOTSUP, "batch too large for one launch");
         dim3 grid((unsigned)gx, (unsigned)r.count, 1), block((unsigned)r.nt, 1, 1);
         ProfScope prof(p, st, INVERSE ? 1 : 0, k, 10 * (r.nt / 256) + r.tcl, r.elems);
@@ -429,9 +448,15 @@ static int run_tb_level(const snfft_plan* p, int k, const void* in, void* out, l
 #define SNFFT_TB_LAUNCH(NT_, MINB_, MB, MAXIN)                                  \
     do {                                                                        \
         if (INVERSE) {                                                          \
-            auto kfn = inv_tb_kernel<T, NT_, MINB_, MB, MAXIN, TB_NBUF>;        \
-            if ((rc = set_smem(kfn, smem))) return rc;                          \
-            SNFFT_LAUNCH(kfn, grid, block, smem, st, a);                        \
+            if (MAXIN == 1 && nbuf == TB_NBUF_ALL) {                            \
+                auto kfn = inv_tb_kernel<T, NT_, MINB_, MB, 1, TB_NBUF_ALL>;    \
+                if ((rc = set_smem(kfn, smem))) return rc;                      \
+                SNFFT_LAUNCH(kfn, grid, block, smem, st, a);                    \
+            } else {                                                            \
+                auto kfn = inv_tb_kernel<T, NT_, MINB_, MB, MAXIN, TB_NBUF>;    \
+                if ((rc = set_smem(kfn, smem))) return rc;                      \
+                SNFFT_LAUNCH(kfn, grid, block, smem, st, a);                    \
+            }                                                                   \
         } else {                                                                \
             auto kfn = fwd_tb_kernel<T, NT_, MINB_, MB, MAXIN, TB_NBUF>;        \
             if ((rc = set_smem(kfn, smem))) return rc;                          \

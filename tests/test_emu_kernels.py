@@ -235,3 +235,27 @@ def test_vector_gather_scatter(emu, n, B, dt):
     finally:
         emu.snfft_debug_scalar_gather(0)
         emu.snfft_plan_destroy(plan)
+
+
+def test_tb_forward_persistent_tiles(emu, monkeypatch):
+    """The forward TB kernel walks over several tiles per CTA (tables staged once, the next tile's inputs
+    prefetched behind the last B phase): with the grid capped at one CTA per task every tile goes through
+    the loop, and the result must not change."""
+    n, B = 7, 44
+    rng = np.random.default_rng(44)
+    f = rng.standard_normal((B, math.factorial(n)))
+    abi = CAbi(emu)
+    plan = abi.plan(n, np.float64)
+    try:
+        ref = abi.forward(plan, f)
+        monkeypatch.setenv("SNFFT_TB_GX", "1")
+        one = abi.forward(plan, f)
+        monkeypatch.setenv("SNFFT_TB_GX", "2")
+        two = abi.forward(plan, f)
+        assert np.array_equal(ref, one) and np.array_equal(ref, two)
+        want = O.sn_fft_packed(f[:2], n)
+        got = unpack(ref, n, B)
+        for lam in want:
+            assert rel_err(got[lam][:2], want[lam]) < 1e-12, lam
+    finally:
+        emu.snfft_plan_destroy(plan)
