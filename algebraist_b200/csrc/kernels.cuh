@@ -1020,6 +1020,33 @@ __global__ void __launch_bounds__(256) gather_vec_kernel(const T* __restrict__ i
 }
 
 // ---------------------------------------------------------------------------
+// calc_power (fourier.py:362-393): power[lambda][b] = d_lambda / n! * || F_lambda[b] ||_F^2 on the packed
+// coefficients [lambda][B][d][d].   grid (partitions, B), 256 threads, fp64 accumulation
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) power_kernel(const T* __restrict__ F, const long long* __restrict__ coef_off,
+                                                   const int* __restrict__ dims, long long batch, double inv_order,
+                                                   T* __restrict__ out) {
+    __shared__ double part[256];
+    const int lam = blockIdx.x;
+    const long long b = blockIdx.y;
+    const long long lo = coef_off[lam], dd = coef_off[lam + 1] - lo;
+    const T* __restrict__ src = F + lo * batch + b * dd;
+    double acc = 0.0;
+    for (long long e = threadIdx.x; e < dd; e += 256) {
+        const double v = (double)src[e];
+        acc += v * v;
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[(long long)lam * batch + b] = (T)(part[0] * (double)dims[lam] * inv_order);
+}
+
+// ---------------------------------------------------------------------------
 // index kernels (bit exact)
 // ---------------------------------------------------------------------------
 __global__ void perm_rank_kernel(const int8_t* __restrict__ perms, long long m, long long* __restrict__ ranks,

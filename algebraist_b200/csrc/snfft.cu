@@ -143,6 +143,7 @@ struct snfft_plan {
     IndexArgs ia;
     void* d_p1 = nullptr;               // chain index of every rank (uint32), n <= 11; larger n compute it per tile
     void* d_coef_off = nullptr;         // device copy of the level-n coefficient offsets (pack / unpack)
+    void* d_dims = nullptr;             // device copy of d_lambda per partition of level n (snfft_power)
     void* d_tile_prefix = nullptr;      // first 32-coefficient tile of every partition (pack / unpack grid)
     long long n_pack_tiles = 0;
     void *d_vtile_prefix32 = nullptr, *d_vtile_prefix64 = nullptr;   // the same for pack_vec_kernel (128 / 64 coefficients)
@@ -861,6 +862,10 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
             }
             p->n_pack_tiles = t;
             int rc = upload(p, offs, &p->d_coef_off);
+            if (!rc) {
+                std::vector<int> dm(L.dims.begin(), L.dims.end());
+                rc = upload(p, dm, &p->d_dims);
+            }
             if (!rc) rc = upload(p, pre, &p->d_tile_prefix);
             for (int tr : {128, 64}) {
                 std::vector<long long> vpre;
@@ -1012,6 +1017,30 @@ int snfft_forward_cosets(const snfft_plan_t* pn, const snfft_plan_t* pm, const v
         return set_error(SNFFT_EWORKSPACE, "workspace too small");
     return pn->dtype == SNFFT_F32 ? forward_cosets_impl<float>(pn, pm, f, B, cosets, ncosets, F, ws, st)
                                   : forward_cosets_impl<double>(pn, pm, f, B, cosets, ncosets, F, ws, st);
+}
+
+int snfft_power(const snfft_plan_t* p, const void* F, int64_t B, void* out, void* stream) {
+    if (!p) return set_error(SNFFT_EINVAL, "plan is NULL");
+    if (B < 0) return set_error(SNFFT_EINVAL, "negative batch");
+    if (B == 0) return SNFFT_OK;
+    if (!F || !out) return set_error(SNFFT_EINVAL, "NULL data pointer");
+    if (B > 65535) return set_error(SNFFT_ENOTSUP, "snfft_power: batch above 65535");
+    const HostLevel& L = p->host.levels[p->n];
+    dim3 grid((unsigned)L.shapes.size(), (unsigned)B, 1), block(256, 1, 1);
+    const double inv_order = 1.0 / (double)p->host.factorial[p->n];
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->dtype == SNFFT_F32) {
+        auto kfn = power_kernel<float>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const float*)F, (const long long*)p->d_coef_off, (const int*)p->d_dims,
+                     (long long)B, inv_order, (float*)out);
+    } else {
+        auto kfn = power_kernel<double>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const double*)F, (const long long*)p->d_coef_off, (const int*)p->d_dims,
+                     (long long)B, inv_order, (double*)out);
+    }
+    g_launches.fetch_add(1);
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
 }
 
 int snfft_inverse(const snfft_plan_t* p, const void* F, int64_t B, void* f, void* ws, size_t ws_bytes, void* stream) {

@@ -150,6 +150,43 @@ def sn_ifft(ft: dict, n: int) -> torch.Tensor:
     return out if home == out.device else out.to(home)
 
 
+def sn_fourier_decomposition(ft: dict, n: int) -> dict:
+    """Per-partition components of the inverse transform (reference fourier.py:291-295):
+    {lambda: d_lambda/n! <F(lambda), rho_lambda(.)>}, whose sum over lambda is sn_ifft(ft, n).
+    Each component is the inverse pipeline run on the coefficients of one partition with every other
+    block zero (the reference's own recursion raises for n > 5, fourier.py:202-214)."""
+    plan, packed, batch, lead, home = _pack_ft(ft, n)
+    one = torch.zeros_like(packed)
+    out = {}
+    for lam, d, off in zip(plan.partitions, plan.dims, plan.offsets):
+        blk = slice(off * batch, (off + d * d) * batch)
+        one[blk].copy_(packed[blk])
+        comp = _inverse_packed(plan, one, batch).view(lead + (plan.nfact,))
+        one[blk].zero_()
+        if n <= BASE_CASE:
+            comp = comp.squeeze()
+        out[lam] = comp if home == comp.device else comp.to(home)
+    return out
+
+
+def calc_power(ft: dict, n: int) -> dict:
+    """Power spectrum {lambda: d_lambda/n! ||F(lambda)||_F^2} (reference fourier.py:349-393): shape () per
+    partition for an unbatched ft, (batch,) for a batched one.  The values add up to ||f||^2."""
+    plan, packed, batch, lead, home = _pack_ft(ft, n)
+    if len(lead) > 1:
+        raise ValueError("calc_power takes an unbatched or a singly batched ft like the reference")
+    out = torch.empty((len(plan.partitions), batch), dtype=packed.dtype, device=packed.device)
+    if batch:
+        with _device_ctx(packed.device):
+            _lib.check(_lib.load().snfft_power(plan.handle, packed.data_ptr(), batch, out.data_ptr(),
+                                               _stream_ptr(packed.device)), "snfft_power")
+    result = {}
+    for p, lam in enumerate(plan.partitions):
+        v = out[p].view(lead)
+        result[lam] = v if home == v.device else v.to(home)
+    return result
+
+
 def _dense_rep(plan, part: int) -> torch.Tensor:
     d = plan.dims[part]
     out = torch.empty((plan.nfact, d, d), dtype=plan.dtype, device=plan.device)

@@ -115,6 +115,13 @@ int snfft_inverse(const snfft_plan_t* plan, const void* F, int64_t B, void* f,
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Power spectrum of packed coefficients: out[lambda][b] = d_lambda / n! * ||F_lambda[b]||_F^2
+ * (calc_power / _calc_power, fourier.py:349-393; the entries add up to ||f_b||^2, Plancherel).
+ * out: [n_partitions][B] in the plan's dtype.  B <= 65535.
+ */
+int snfft_power(const snfft_plan_t* plan, const void* F, int64_t B, void* out, void* stream);
+
+/*
  * Partial forward transform over a subset of the top-level cosets
  * {sigma : sigma[i] = n-1} (the coset-sharded transform of one large function,
  * SURVEY 8e / BASELINE config 5):

@@ -94,3 +94,22 @@ if __name__ == "__main__":
         tables()
         for n in range(2, 8):
             transforms(n, 3, both)
+
+
+def next_rows():
+    """tests/golden/next_rows.npz: sn_fourier_decomposition (fourier.py:291-295) and calc_power
+    (fourier.py:362-393) of the UNMODIFIED reference on the ft of transform_n{n}.npz, n = 3..5
+    (the reference's recursive inverse only works for n <= 5)."""
+    out = {}
+    for n in range(3, 6):
+        torch.manual_seed(1000 + n)
+        f = torch.randn(3, math.factorial(n), dtype=torch.float64)
+        ft = RF.sn_fft(f, n)
+        for lam, v in RF.sn_fourier_decomposition(ft, n).items():
+            out[f"n{n}_decomp_{key(lam)}"] = v.numpy()
+        for lam, v in RF.calc_power(ft, n).items():
+            out[f"n{n}_power_{key(lam)}"] = v.numpy()
+        one = {lam: v[0] for lam, v in ft.items()}            # unbatched call
+        for lam, v in RF.calc_power(one, n).items():
+            out[f"n{n}_power1_{key(lam)}"] = np.asarray(v.numpy())
+    np.savez_compressed(os.path.join(OUT, "next_rows.npz"), **out)

@@ -111,3 +111,52 @@ def test_errors(emu):
             A.sn_fft(torch.randn(1), 1)
         with pytest.raises(ValueError):
             A.sn_ifft({(5,): torch.randn(1)}, 5)
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+def test_decomposition_and_power_vs_reference(emu, n):
+    """sn_fourier_decomposition (fourier.py:291-295) and calc_power (fourier.py:349-393) against the
+    unmodified reference (tests/golden/next_rows.npz, made by oracle/make_golden.py)."""
+    import os
+    import algebraist_b200 as A
+    from conftest import GOLDEN
+    g = load_transform_golden(n)
+    nx = np.load(os.path.join(GOLDEN, "next_rows.npz"))
+    f = torch.from_numpy(g[f"n{n}_f64_f"])
+    with package_on_emu(emu):
+        ft = A.sn_fft(f, n)
+        dec = A.sn_fourier_decomposition(ft, n)
+        assert list(dec.keys()) == list(O.generate_partitions(n))
+        total = 0
+        for lam, v in dec.items():
+            ref = nx[f"n{n}_decomp_{key(lam)}"]
+            assert tuple(v.shape) == ref.shape
+            assert np.allclose(v.numpy(), ref, atol=1e-12), lam
+            total = total + v
+        assert np.allclose(total.numpy(), f.numpy(), atol=1e-12)           # reference tests/test_fourier.py:66-72
+        pw = A.calc_power(ft, n)
+        for lam, v in pw.items():
+            ref = nx[f"n{n}_power_{key(lam)}"]
+            assert tuple(v.shape) == ref.shape and np.allclose(v.numpy(), ref, rtol=1e-12), lam
+        assert np.allclose(sum(pw.values()).numpy(), (f ** 2).sum(1).numpy())   # tests/test_fourier.py:75-84
+        one = A.sn_fft(f[0], n)
+        pw1 = A.calc_power(one, n)
+        for lam, v in pw1.items():
+            ref = nx[f"n{n}_power1_{key(lam)}"]
+            assert tuple(v.shape) == ref.shape and np.allclose(v.numpy(), ref, rtol=1e-12), lam
+
+
+def test_decomposition_large_n(emu):
+    """n = 6 (the reference raises there): the components still add up to the inverse transform and
+    Plancherel holds for calc_power."""
+    import algebraist_b200 as A
+    n = 6
+    torch.manual_seed(6)
+    f = torch.randn(2, math.factorial(n), dtype=torch.float64)
+    with package_on_emu(emu):
+        ft = A.sn_fft(f, n)
+        dec = A.sn_fourier_decomposition(ft, n)
+        assert np.allclose(sum(dec.values()).numpy(), f.numpy(), atol=1e-12)
+        pw = A.calc_power(ft, n)
+        assert all(tuple(v.shape) == (2,) for v in pw.values())
+        assert np.allclose(sum(pw.values()).numpy(), (f ** 2).sum(1).numpy())

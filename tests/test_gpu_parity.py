@@ -276,3 +276,24 @@ def test_vs_oracle_n11(A):
     ref = O.sn_fft_packed_c(f, n)
     ft = A.sn_fft(torch.from_numpy(f[0]).float().cuda(), n)
     _check_dict(ft, ref, TOL["f32"])
+
+
+@pytest.mark.parametrize("n,dt", [(5, "f64"), (7, "f32"), (8, "f64")])
+def test_decomposition_and_power_gpu(A, n, dt):
+    """sn_fourier_decomposition / calc_power on the device: reference goldens at n = 5, and at every n the
+    components add up to f and the power spectrum adds up to ||f||^2 (reference tests/test_fourier.py:66-84)."""
+    import os
+    from conftest import GOLDEN
+    torch.manual_seed(1000 + n)
+    f = torch.randn(3, math.factorial(n), dtype=torch.float64).to(TDT[dt]).cuda()
+    ft = A.sn_fft(f, n)
+    dec = A.sn_fourier_decomposition(ft, n)
+    assert rel_err(sum(dec.values()).cpu().numpy(), f.cpu().numpy()) < TOL[dt]
+    pw = A.calc_power(ft, n)
+    tot = sum(v.double() for v in pw.values())
+    assert ((tot - f.double().pow(2).sum(1)).abs() / tot).max().item() < 10 * TOL[dt]
+    if n == 5:
+        nx = np.load(os.path.join(GOLDEN, "next_rows.npz"))
+        for lam in dec:
+            assert np.allclose(dec[lam].cpu().numpy(), nx[f"n5_decomp_{key(lam)}"], atol=1e-12)
+            assert np.allclose(pw[lam].cpu().numpy(), nx[f"n5_power_{key(lam)}"], rtol=1e-12)
