@@ -877,7 +877,12 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
                 if (!rc) rc = upload(p, vpre, tr == 128 ? &p->d_vtile_prefix32 : &p->d_vtile_prefix64);
                 (tr == 128 ? p->n_vtiles32 : p->n_vtiles64) = vt;
             }
-            if (!rc && n >= 4 && n <= 11) {       // 4 * n! bytes: 160 MB at n = 11
+#ifdef SNFFT_HOST_EMU
+            const int p1_max_n = 7;               // the emulation runs one fiber per rank: keep the table small there
+#else
+            const int p1_max_n = 11;
+#endif
+            if (!rc && n >= 4 && n <= p1_max_n) {       // 4 * n! bytes: 160 MB at n = 11
                 void* d = nullptr;
                 if (cudaMalloc(&d, (size_t)p->ia.nfact * sizeof(uint32_t)) == cudaSuccess) {
                     p->allocs.push_back(d);

@@ -62,6 +62,23 @@ def workload_name(a):
     return f"S{a.n} {a.dtype} FFT+IFFT, batch {a.batch} per GPU"
 
 
+def measured_traffic(kernel, batch, dtype):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/*traffic*.json, written by
+    tools/ncu_traffic.py from `ncu --set full`), or None when no capture matches this workload."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        for fn in sorted(os.listdir(pdir)):
+            if "traffic" in fn and fn.endswith(".json"):
+                with open(os.path.join(pdir, fn)) as fh:
+                    for rec in json.load(fh):
+                        if rec.get("kernel") == kernel and rec.get("batch") == batch and rec.get("dtype") == dtype:
+                            best = {"bytes": rec["dram_bytes_per_launch"], "source": "profiles/" + fn}
+    except Exception:
+        return None
+    return best
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -274,11 +291,12 @@ def run_native(a):
             bytes_per_launch = 2 * r.elems_per_instance * ninst * esize
             avg_ms = r.total_ms / r.launches
             kernels.append({"kernel": f"{kinds[r.kind]}_k{r.level}_c{r.kernel_class}", "launches": r.launches,
-                            "avg_ms": avg_ms, "share": r.total_ms / ms,
+                            "avg_ms": avg_ms, "share": r.total_ms / ms, "alg_bytes": bytes_per_launch,
                             "alg_gbs": bytes_per_launch / (avg_ms * 1e-3) / 1e9})
         kernels.sort(key=lambda k: -k["share"])
         top = kernels[0]
         alg_bytes_pair = 4 * nf * esize
+        traffic = measured_traffic(top["kernel"], B, a.dtype)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -287,7 +305,10 @@ def run_native(a):
                        "l2_policy": f"inputs larger than L2 ({B * nf * esize / 1e6:.0f} MB per array per GPU)",
                        "round_trip_rel_err": err},
             "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": top["alg_gbs"], "peak": peak,
-                         "unit": "GB/s", "frac": top["alg_gbs"] / peak, "traffic": None,
+                         "unit": "GB/s", "frac": top["alg_gbs"] / peak,
+                         "traffic": traffic["bytes"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None,
+                         "algorithmic_bytes_per_launch": top["alg_bytes"],
                          "peak_source": peak_src, "kernel_share_of_step": top["share"],
                          "end_to_end_alg_gbs": value / world * alg_bytes_pair / 1e9,
                          "end_to_end_frac": value / world * alg_bytes_pair / 1e9 / peak},

@@ -1,0 +1,42 @@
+"""Write profiles/<name>_traffic.json from the summary CSV of an `ncu --set full` capture of
+tools/prof_step.py (tools/ncu_summary.py): DRAM read + write bytes per launch of the kernels the bench
+line names.  The level kernels of one forward + inverse run in a fixed order, so the k-th launch of a
+kernel family is matched to the bench name by its template arguments and grid.
+
+    python tools/ncu_traffic.py summary.csv batch dtype out.json
+"""
+import csv
+import json
+import sys
+
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def to_bytes(s):
+    v, u = s.split()
+    return float(v) * UNIT[u]
+
+
+def main():
+    rows = list(csv.reader(open(sys.argv[1])))
+    batch, dtype, out = int(sys.argv[2]), sys.argv[3], sys.argv[4]
+    h = rows[0]
+    ki, ti, ri, wi = h.index("kernel"), h.index("time"), h.index("dram_rd"), h.index("dram_wr")
+    recs = []
+    # dominant kernels of the bench line: the largest launch of each sweep-kernel class, by family
+    fam = {"inv_level_kernel<float, 4, 4, 128": "inv_level_k10_c3", "fwd_level_kernel<float, 4, 4, 128": "fwd_level_k10_c3",
+           "inv_level_kernel<double, 2, 4, 128": "inv_level_k10_c3", "fwd_level_kernel<double, 2, 4, 128": "fwd_level_k10_c3"}
+    best = {}
+    for r in rows[1:]:
+        for pat, name in fam.items():
+            if r[ki].startswith(pat):
+                t = float(r[ti].split()[0])
+                if name not in best or t > best[name][0]:
+                    best[name] = (t, to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
+    for name, (t, b, ts) in best.items():
+        recs.append({"kernel": name, "batch": batch, "dtype": dtype, "dram_bytes_per_launch": b, "ncu_time": ts})
+    json.dump(recs, open(out, "w"), indent=1)
+    print(recs)
+
+
+main()
