@@ -297,3 +297,15 @@ def test_decomposition_and_power_gpu(A, n, dt):
         for lam in dec:
             assert np.allclose(dec[lam].cpu().numpy(), nx[f"n5_decomp_{key(lam)}"], atol=1e-12)
             assert np.allclose(pw[lam].cpu().numpy(), nx[f"n5_power_{key(lam)}"], rtol=1e-12)
+
+
+def test_stream_batches_host_pipeline(A):
+    """Host-resident batch streamed through the GPU in chunks (ragged last chunk): same result as one call."""
+    n, B = 8, 37
+    torch.manual_seed(3)
+    f_host = torch.randn(B, math.factorial(n)).pin_memory()
+    out = A.stream_batches(lambda x: A.sn_ifft(A.sn_fft(x, n), n), f_host, chunk=8)
+    assert out.shape == f_host.shape and rel_err(out.numpy(), f_host.numpy()) < TOL["f32"]
+    ft_host = A.stream_batches(lambda x: A.sn_fft(x, n)[(n - 1, 1)], f_host, chunk=16)
+    ref = A.sn_fft(f_host.cuda(), n)[(n - 1, 1)].cpu()
+    assert torch.equal(ft_host, ref)

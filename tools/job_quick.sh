@@ -1,3 +1,5 @@
-SNFFT_TB_FWD= SNFFT_TB_INV= python bench.py --steps 3 --warmup 3 --no-cpu-baseline --dtype f64 > gpurun_out/bench_d0.json 2> gpurun_out/bench_d0.err; echo "bench rc=$?"
-SNFFT_TB_FWD=7,8,9,10 SNFFT_TB_INV=7,8,9,10 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --dtype f64 > gpurun_out/bench_d1.json 2> gpurun_out/bench_d1.err; echo "bench rc=$?"
-SNFFT_TB_WAVES=0 SNFFT_TB_FWD=7,8,9,10 SNFFT_TB_INV=7,8,9,10 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --dtype f64 > gpurun_out/bench_d2.json 2> gpurun_out/bench_d2.err; echo "bench rc=$?"
+for c in 8 16 32; do
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-chunk $c > gpurun_out/bench_e2e_$c.json 2> gpurun_out/bench_e2e_$c.err; echo "bench $c rc=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/bench_e2e_$c.json')); print($c, d['value'], d['e2e']['value'])"
+done
