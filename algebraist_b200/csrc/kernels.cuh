@@ -29,7 +29,7 @@ namespace snfft {
 //   [k-1, 2(k-1))   npairs_j | nneg_j << 16
 //   entries of j    npairs_j rotations  t1 | t2 << 13 | code << 26, then nneg_j rows to negate
 // restricted to the rows the column can occupy before step j (see build_level).
-// `code` indexes LevelArgs::lut: a = lut[code] = 1/d, b = lut[LUT + code] = sqrt(1 - 1/d^2)
+// `code` indexes LevelArgs::lut: a = lut[code] = 1/d, b = lut[LUT + code] = sqrt(1 - 1/d^2) (interleaved in shared memory)
 // for the signed axial distance d (irreps.py:91-109):  x1' = a x1 + b x2 ; x2' = b x1 - a x2.
 constexpr int LUT = 24;
 
@@ -167,7 +167,8 @@ __device__ __forceinline__ void sweep(T* __restrict__ work, int bstride, int nac
     for (int p = rg; p < npairs; p += G) {
         const uint32_t e = ent[p];
         const int o1 = (int)(e & 0x1fffu) * TC, o2 = (int)((e >> 13) & 0x1fffu) * TC;
-        const T ca = lut[e >> 26], cb = lut[LUT + (e >> 26)];
+        const Pack<T, 2> cab = *reinterpret_cast<const Pack<T, 2>*>(lut + 2 * (e >> 26));     // interleaved (a, b)
+        const T ca = cab.v[0], cb = cab.v[1];
         P x1[NBUF], x2[NBUF];
 #pragma unroll
         for (int m = 0; m < NBUF; ++m)
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
     const int bstride = a.bstride;
     T* __restrict__ work = reinterpret_cast<T*>(smem_raw) + (size_t)grp * NBUF * bstride;
     T* __restrict__ lut = reinterpret_cast<T*>(smem_raw) + (size_t)NG * NBUF * bstride;
-    if (tid < 2 * LUT) lut[tid] = a.lut[tid];
+    if (tid < 2 * LUT) lut[tid] = a.lut[(tid & 1) * LUT + (tid >> 1)];      // shared copy interleaves (a, b) per code
     const uint32_t* __restrict__ tab = stage_table<STAGE>(reinterpret_cast<uint32_t*>(lut + 2 * LUT), a.tables,
                                                           tk.tab_off, tk.tab_words, tid, W * G * NG);
     __syncthreads();
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
     const int bstride = a.bstride;
     T* __restrict__ work = reinterpret_cast<T*>(smem_raw) + (size_t)grp * NBUF * bstride;
     T* __restrict__ lut = reinterpret_cast<T*>(smem_raw) + (size_t)NG * NBUF * bstride;
-    if (tid < 2 * LUT) lut[tid] = a.lut[tid];
+    if (tid < 2 * LUT) lut[tid] = a.lut[(tid & 1) * LUT + (tid >> 1)];      // shared copy interleaves (a, b) per code
 
     P acc[NBUF][RPT];
 #pragma unroll
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(NW * 32) base_kernel(const BaseArgs<T> a) {
         const int pk = (int)(a.fact[k0] / a.fact[k]);       // P_k
         __syncthreads();                                    // previous level done, old table free
         for (int w = tid; w < L.tab_words; w += NW * 32) tab_s[w] = L.tables[w];
-        if (tid < 2 * LUT) lut[tid] = L.lut[tid];
+        if (tid < 2 * LUT) lut[tid] = L.lut[(tid & 1) * LUT + (tid >> 1)];
         __syncthreads();
         if (!INVERSE) {
             for (int t = 0; t < L.nftasks; ++t) {
