@@ -7,7 +7,7 @@
 //   (chain prefix p_k, batch b): inst_k = p_k * B + b, and the k cosets of
 //   S_{k-1} in S_k (fourier.py:63-80) are the planes
 //   inst_{k-1} = i * NINST_k + inst_k.
-//   X_n is stored in the public packed layout [lambda][B][d][d] instead.
+//   (X_n included; pack_kernel converts it to the public packed layout.)
 //
 // One forward level step (fourier.py:253-273) for output column c of block b
 // of F_lambda:
@@ -58,7 +58,6 @@ struct LevelArgs {
     const InvParent* parents;
     const uint32_t* tables;
     int k;
-    int cw, ci;                   // column x instance tile of the packed-layout level (cw * ci == TC)
     int bstride;                  // elements of one work buffer (rows * TC)
     int tab_smem_words;           // shared-memory words reserved for one task table
     long long ninst;              // NINST_k
@@ -231,60 +230,34 @@ __device__ __forceinline__ void group_sync() {
 
 // Column tile bookkeeping shared by the forward and inverse kernels.
 // A tile is TC = W * V "slots"; a slot is one (column c, instance) pair of the
-// task's child block.  Threads have two roles:
+// task's child block, enumerated instance-fastest over the flattened (c, inst)
+// range.  Threads have two roles:
 //   transfer role: moves rows between global and shared memory.  Scalar form:
-//                  slot fs = lt % TC, rows fr, fr + FR, ...; vector form (intermediate
-//                  levels with NINST % TV == 0): TV = 16 / sizeof(T) adjacent slots
-//                  (= adjacent instances of one column, 16 aligned bytes) per thread.
+//                  slot fs = lt % TC, rows fr, fr + FR, ...; vector form (NINST % TV == 0):
+//                  TV = 16 / sizeof(T) adjacent slots (= adjacent instances of one
+//                  column, 16 aligned bytes) per thread.
 //   sweep role   : V slots lane*V.., rows / rotations rg, rg + G, ...
-// Intermediate levels enumerate slots instance-fastest over the flattened
-// (c, inst) range; the packed-layout level uses a cw x ci tile and two slot
-// orders so that both its loads and its stores are contiguous.
 struct SlotMap {
-    long long c_ld, inst_ld, c_st, inst_st;   // (column, instance) of this thread's slot when loading / storing
-    int src_slot;                             // slot (load order) that holds the (c_st, inst_st) data
-    bool ok_ld, ok_st;
+    long long c, inst;      // (column, instance) of this thread's first transfer slot
+    bool ok;                // inside the range
 };
 
-template <int TC, bool PACKED_IS_INPUT>
-__device__ __forceinline__ SlotMap make_slots(bool packed, long long chunk, int fs, int d_mu, long long ninst,
-                                              long long batch, int cw, int ci, long long* nchunks) {
+template <int TC>
+__device__ __forceinline__ SlotMap make_slots(long long chunk, int fs, int d_mu, long long ninst, long long* nchunks) {
     SlotMap s;
-    if (packed) {
-        const long long ncx = (d_mu + cw - 1) / cw, nbx = (batch + ci - 1) / ci;
-        *nchunks = ncx * nbx;
-        // neighbouring CTAs complete each other's partial sectors on the scattered side:
-        // the forward (packed output) walks columns first, the inverse (packed input) instances first
-        const long long cx = PACKED_IS_INPUT ? chunk / nbx : chunk % ncx;
-        const long long bx = PACKED_IS_INPUT ? chunk % nbx : chunk / ncx;
-        // instance-fastest order: slot = c_rel * ci + i_rel ; column-fastest order: slot = i_rel * cw + c_rel
-        const long long c_if = cx * cw + fs / ci, i_if = bx * ci + fs % ci;
-        const long long c_cf = cx * cw + fs % cw, i_cf = bx * ci + fs / cw;
-        if (PACKED_IS_INPUT) {            // load column-fastest (packed input), store instance-fastest
-            s.c_ld = c_cf; s.inst_ld = i_cf; s.c_st = c_if; s.inst_st = i_if;
-            s.src_slot = (fs % ci) * cw + fs / ci;
-        } else {                          // load instance-fastest, store column-fastest (packed output)
-            s.c_ld = c_if; s.inst_ld = i_if; s.c_st = c_cf; s.inst_st = i_cf;
-            s.src_slot = (fs % cw) * ci + fs / cw;
-        }
-        s.ok_ld = chunk < *nchunks && s.c_ld < d_mu && s.inst_ld < batch;
-        s.ok_st = chunk < *nchunks && s.c_st < d_mu && s.inst_st < batch;
-    } else {
-        const long long qn = (long long)d_mu * ninst;
-        *nchunks = (qn + TC - 1) / TC;
-        const long long q = chunk * TC + fs;
-        s.c_ld = s.c_st = q / ninst;
-        s.inst_ld = s.inst_st = q % ninst;
-        s.src_slot = fs;
-        s.ok_ld = s.ok_st = q < qn;
-    }
+    const long long qn = (long long)d_mu * ninst;
+    *nchunks = (qn + TC - 1) / TC;
+    const long long q = chunk * TC + fs;
+    s.c = q / ninst;
+    s.inst = q % ninst;
+    s.ok = q < qn;
     return s;
 }
 
 // ---------------------------------------------------------------------------
 // forward level step S_{k-1} -> S_k      grid (chunks, tasks)
 // ---------------------------------------------------------------------------
-template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE, bool FINAL>
+template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE>
 __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelArgs<T> a) {
     SNFFT_DYN_SMEM(smem_raw);
     constexpr int TC = W * V, GT = W * G, FR = GT / TC;
@@ -301,12 +274,12 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
     const long long ninst = a.ninst, ninst_prev = a.ninst * nch;
     // 16-byte transfers need alignment; with G == 1 nothing synchronises the lanes, so every
     // thread may only touch its own slot (scalar role)
-    const bool vec = G > 1 && !FINAL && (ninst % TV == 0);
+    const bool vec = G > 1 && (ninst % TV == 0);
     const int fs = vec ? (lt % NVS) * TV : lt % TC;     // first slot this thread transfers
     const int fr = vec ? lt / NVS : lt / TC, frs = vec ? FRV : FR;
 
     long long nchunks;
-    const SlotMap sm = make_slots<TC, false>(FINAL, chunk, fs, tk.d_mu, ninst, a.batch, a.cw, a.ci, &nchunks);
+    const SlotMap sm = make_slots<TC>(chunk, fs, tk.d_mu, ninst, &nchunks);
     if ((long long)blockIdx.x * NG >= nchunks) return;          // whole CTA idle
 
     const int bstride = a.bstride;
@@ -316,7 +289,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
     const uint32_t* __restrict__ tab = stage_table<STAGE>(reinterpret_cast<uint32_t*>(lut + 2 * LUT), a.tables,
                                                           tk.tab_off, tk.tab_words, tid, W * G * NG);
     __syncthreads();
-    const T* __restrict__ src = a.in + (tk.mu_off + sm.c_ld) * ninst_prev + sm.inst_ld;
+    const T* __restrict__ src = a.in + (tk.mu_off + sm.c) * ninst_prev + sm.inst;
     const long long rstride = (long long)tk.d_mu * ninst_prev;
 
     P acc[RPT];
@@ -335,7 +308,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
             const int zs = (lt % NVS) * TV;
             for (int t = lt / NVS; t < tk.d_lam; t += FRV) {
                 const int rr = t - tk.boff;
-                if (rr >= 0 && rr < tk.d_mu && sm.ok_ld && vec) continue;      // filled by the copies below
+                if (rr >= 0 && rr < tk.d_mu && sm.ok && vec) continue;      // filled by the copies below
                 if (rr >= 0 && rr < tk.d_mu && !vec) continue;
 #pragma unroll
                 for (int m = 0; m < NBUF; ++m)
@@ -351,7 +324,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
             }
         }
         if (vec) {
-            if (sm.ok_ld) {
+            if (sm.ok) {
                 const T* __restrict__ p = src + (long long)fr * rstride + (long long)i0 * ninst;
                 T* __restrict__ w = work + (tk.boff + fr) * TC + fs;
                 for (int r = fr; r < tk.d_mu; r += FRV, p += (long long)FRV * rstride, w += FRV * TC) {
@@ -366,7 +339,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
                 for (int m = 0; m < NBUF; ++m)
                     if (m < nb) {
                         T* w = work + m * bstride + (tk.boff + r) * TC + fs;
-                        if (sm.ok_ld) copy_async(w, src + r * rstride + (i0 + m) * ninst);
+                        if (sm.ok) copy_async(w, src + r * rstride + (i0 + m) * ninst);
                         else *w = T(0);
                     }
             }
@@ -404,22 +377,16 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
         if (t < tk.d_lam) *reinterpret_cast<P*>(work + t * TC + lane * V) = acc[q];
     }
     __syncthreads();
-    if (sm.ok_st) {
-        if (FINAL) {
-            T* __restrict__ dst = a.out + tk.lam_off * a.batch + sm.inst_st * ((long long)tk.d_lam * tk.d_lam) +
-                                  tk.boff + sm.c_st;
-            for (int t = fr; t < tk.d_lam; t += FR) dst[(long long)t * tk.d_lam] = work[t * TC + sm.src_slot];
+    if (sm.ok) {
+        T* __restrict__ dst = a.out + (tk.lam_off + tk.boff + sm.c) * ninst + sm.inst;
+        const long long ostride = (long long)tk.d_lam * ninst;
+        if (vec) {
+            dst += (long long)fr * ostride;
+            const T* __restrict__ w = work + fr * TC + fs;
+            for (int t = fr; t < tk.d_lam; t += FRV, dst += (long long)FRV * ostride, w += FRV * TC)
+                *reinterpret_cast<PV*>(dst) = *reinterpret_cast<const PV*>(w);
         } else {
-            T* __restrict__ dst = a.out + (tk.lam_off + tk.boff + sm.c_st) * ninst + sm.inst_st;
-            const long long ostride = (long long)tk.d_lam * ninst;
-            if (vec) {
-                dst += (long long)fr * ostride;
-                const T* __restrict__ w = work + fr * TC + fs;
-                for (int t = fr; t < tk.d_lam; t += FRV, dst += (long long)FRV * ostride, w += FRV * TC)
-                    *reinterpret_cast<PV*>(dst) = *reinterpret_cast<const PV*>(w);
-            } else {
-                for (int t = fr; t < tk.d_lam; t += FR) dst[t * ostride] = work[t * TC + sm.src_slot];
-            }
+            for (int t = fr; t < tk.d_lam; t += FR) dst[t * ostride] = work[t * TC + fs];
         }
     }
 }
@@ -431,7 +398,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) fwd_level_kernel(const LevelAr
 // The coset group index is the fastest grid dimension so that the CTAs that
 // re-read one column tile of F_lambda run together and hit in L2.
 // ---------------------------------------------------------------------------
-template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE, bool FIRST>
+template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE>
 __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelArgs<T> a) {
     SNFFT_DYN_SMEM(smem_raw);
     constexpr int TC = W * V, GT = W * G, FR = GT / TC;
@@ -450,12 +417,12 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
     const long long cblock = blockIdx.x / ngroups;
     const long long chunk = cblock * NG + grp;
     const long long ninst = a.ninst, ninst_prev = a.ninst * k;
-    const bool vec = G > 1 && !FIRST && (ninst % TV == 0);
+    const bool vec = G > 1 && (ninst % TV == 0);
     const int fs = vec ? (lt % NVS) * TV : lt % TC;
     const int fr = vec ? lt / NVS : lt / TC;
 
     long long nchunks;
-    const SlotMap sm = make_slots<TC, true>(FIRST, chunk, fs, tk.d_mu, ninst, a.batch, a.cw, a.ci, &nchunks);
+    const SlotMap sm = make_slots<TC>(chunk, fs, tk.d_mu, ninst, &nchunks);
     if (cblock * NG >= nchunks) return;
 
     const int bstride = a.bstride;
@@ -473,15 +440,8 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
 
     for (int p = 0; p < tk.npar; ++p) {
         const InvParent par = a.parents[tk.par_off + p];
-        const T* __restrict__ src;
-        long long rstride;
-        if (FIRST) {
-            src = a.in + par.lam_off * a.batch + sm.inst_ld * ((long long)par.d_lam * par.d_lam) + par.boff + sm.c_ld;
-            rstride = par.d_lam;
-        } else {
-            src = a.in + (par.lam_off + par.boff + sm.c_ld) * ninst + sm.inst_ld;
-            rstride = (long long)par.d_lam * ninst;
-        }
+        const T* __restrict__ src = a.in + (par.lam_off + par.boff + sm.c) * ninst + sm.inst;
+        const long long rstride = (long long)par.d_lam * ninst;
         const uint32_t* __restrict__ tab = stage_table<STAGE>(reinterpret_cast<uint32_t*>(lut + 2 * LUT), a.tables,
                                                               par.tab_off, par.tab_words, tid, W * G * NG);
         if (vec) {
@@ -494,7 +454,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
 #pragma unroll
                 for (int m = 0; m < NBUF; ++m)
                     if (m < nb) {
-                        if (sm.ok_ld) SNFFT_CP_ASYNC(w + m * bstride, q, 16);
+                        if (sm.ok) SNFFT_CP_ASYNC(w + m * bstride, q, 16);
                         else *reinterpret_cast<PV*>(w + m * bstride) = zero;
                     }
             }
@@ -503,7 +463,7 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
 #pragma unroll
                 for (int m = 0; m < NBUF; ++m)
                     if (m < nb) {
-                        if (sm.ok_ld) copy_async(work + m * bstride + t * TC + fs, src + t * rstride);
+                        if (sm.ok) copy_async(work + m * bstride + t * TC + fs, src + t * rstride);
                         else work[m * bstride + t * TC + fs] = T(0);
                     }
             }
@@ -543,19 +503,19 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
             }
         }
     __syncthreads();
-    if (sm.ok_st) {
+    if (sm.ok) {
         const long long ostride = (long long)tk.d_mu * ninst_prev;
 #pragma unroll
         for (int m = 0; m < NBUF; ++m)
             if (m < nb) {
-                T* __restrict__ dst = a.out + (tk.mu_off + sm.c_st) * ninst_prev + (long long)(i0 + m) * ninst + sm.inst_st;
+                T* __restrict__ dst = a.out + (tk.mu_off + sm.c) * ninst_prev + (long long)(i0 + m) * ninst + sm.inst;
                 if (vec) {
                     dst += (long long)fr * ostride;
                     const T* __restrict__ w = work + m * bstride + fr * TC + fs;
                     for (int t = fr; t < tk.d_mu; t += FRV, dst += (long long)FRV * ostride, w += FRV * TC)
                         *reinterpret_cast<PV*>(dst) = *reinterpret_cast<const PV*>(w);
                 } else {
-                    for (int t = fr; t < tk.d_mu; t += FR) dst[t * ostride] = work[m * bstride + t * TC + sm.src_slot];
+                    for (int t = fr; t < tk.d_mu; t += FR) dst[t * ostride] = work[m * bstride + t * TC + fs];
                 }
             }
     }

@@ -361,24 +361,6 @@ struct ProfScope {
     }
 };
 
-// cw x ci tile (columns x instances) of the packed-layout level, cw * ci == TC.
-// The side the kernel LOADS from gets a full 32-byte sector (8 fp32): instances for the forward
-// transform (its input is instance-fastest), columns for the inverse (its input is the packed
-// layout); the store side is completed by the neighbouring CTAs, which L2 merges.
-static void tile_shape(int TC, long long B, bool packed_is_input, int* cw, int* ci) {
-    if (packed_is_input) {
-        int w = std::min(8, TC);
-        while (TC / w > B && w < TC) w *= 2;      // few functions: widen the column side
-        *cw = w;
-        *ci = TC / w;
-    } else {
-        int c = 1;
-        while (c * 2 <= std::min(8, TC) && c * 2 <= B) c *= 2;
-        *ci = c;
-        *cw = TC / c;
-    }
-}
-
 template <typename KF>
 static int set_smem(KF kfn, size_t bytes) {
 #ifndef SNFFT_HOST_EMU
@@ -394,17 +376,9 @@ static int set_smem(KF kfn, size_t bytes) {
 #include "tb_host.inl"
 
 template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE>
-static int launch_fwd_range(const TaskRange& r, bool final_level, LevelArgs<T> a, cudaStream_t st) {
+static int launch_fwd_range(const TaskRange& r, LevelArgs<T> a, cudaStream_t st) {
     constexpr int TC = V * W;
-    long long chunks;
-    if (final_level) {
-        tile_shape(TC, a.batch, false, &a.cw, &a.ci);
-        chunks = ((r.max_dmu + a.cw - 1) / a.cw) * ((a.batch + a.ci - 1) / a.ci);
-    } else {
-        a.cw = TC;
-        a.ci = 1;
-        chunks = ((long long)r.max_dmu * a.ninst + TC - 1) / TC;
-    }
+    const long long chunks = ((long long)r.max_dmu * a.ninst + TC - 1) / TC;
     a.bstride = r.max_dlam * TC;
     a.ftasks += r.begin;
     a.tab_smem_words = STAGE ? r.max_tab : 0;
@@ -412,7 +386,7 @@ static int launch_fwd_range(const TaskRange& r, bool final_level, LevelArgs<T> a
     dim3 grid((unsigned)((chunks + NG - 1) / NG), (unsigned)r.count, 1), block(W * G * NG, 1, 1);
     int rc;
     {
-        auto kfn = fwd_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, false>;
+        auto kfn = fwd_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>;
         if ((rc = set_smem(kfn, smem))) return rc;
         SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
     }
@@ -422,17 +396,9 @@ static int launch_fwd_range(const TaskRange& r, bool final_level, LevelArgs<T> a
 }
 
 template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE>
-static int launch_inv_range(const TaskRange& r, bool first_level, LevelArgs<T> a, cudaStream_t st) {
+static int launch_inv_range(const TaskRange& r, LevelArgs<T> a, cudaStream_t st) {
     constexpr int TC = V * W;
-    long long chunks;
-    if (first_level) {
-        tile_shape(TC, a.batch, true, &a.cw, &a.ci);
-        chunks = ((r.max_dmu + a.cw - 1) / a.cw) * ((a.batch + a.ci - 1) / a.ci);
-    } else {
-        a.cw = TC;
-        a.ci = 1;
-        chunks = ((long long)r.max_dmu * a.ninst + TC - 1) / TC;
-    }
+    const long long chunks = ((long long)r.max_dmu * a.ninst + TC - 1) / TC;
     a.bstride = r.max_dlam * TC;
     a.itasks += r.begin;
     a.tab_smem_words = STAGE ? r.max_tab : 0;
@@ -441,7 +407,7 @@ static int launch_inv_range(const TaskRange& r, bool first_level, LevelArgs<T> a
     dim3 grid((unsigned)(((chunks + NG - 1) / NG) * ngroups), (unsigned)r.count, 1), block(W * G * NG, 1, 1);
     int rc;
     {
-        auto kfn = inv_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE, false>;
+        auto kfn = inv_level_kernel<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>;
         if ((rc = set_smem(kfn, smem))) return rc;
         SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
     }
@@ -465,7 +431,7 @@ static LevelArgs<T> level_args(const snfft_plan* p, int k, const void* in, void*
         a.lut[LUT + c] = (T)D.lut_b[c];
     }
     a.k = k;
-    a.cw = a.ci = a.bstride = a.tab_smem_words = 0;
+    a.bstride = a.tab_smem_words = 0;
     a.ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
     a.batch = B;
     a.nch = k;
@@ -482,14 +448,13 @@ static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, 
         a.nch = nch;
         for (int j = 0; j < nch; ++j) a.cid[j] = cid[j];
     }
-    const bool fin = false;      // the top level is instance-fastest too; pack_kernel converts it
     for (const TaskRange& r : p->lev[k].franges) {
         int rc = SNFFT_ENOTSUP;
         ProfScope prof(p, st, 0, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
             switch (r.cls) {
 #define SNFFT_CASE(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE) \
-    case id: rc = launch_fwd_range<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>(r, fin, a, st); break;
+    case id: rc = launch_fwd_range<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>(r, a, st); break;
                 SNFFT_CLASSES_F32(SNFFT_CASE)
             }
         } else {
@@ -504,14 +469,13 @@ static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, 
 template <typename T>
 static int run_inv_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st) {
     const LevelArgs<T> a = level_args<T>(p, k, in, out, B);
-    const bool first = false;    // unpack_kernel has already made the input instance-fastest
     for (const TaskRange& r : p->lev[k].iranges) {
         int rc = SNFFT_ENOTSUP;
         ProfScope prof(p, st, 1, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
             switch (r.cls) {
 #define SNFFT_CASE(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE) \
-    case id: rc = launch_inv_range<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>(r, first, a, st); break;
+    case id: rc = launch_inv_range<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>(r, a, st); break;
                 SNFFT_CLASSES_F32(SNFFT_CASE)
             }
         } else {
