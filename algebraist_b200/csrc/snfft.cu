@@ -46,24 +46,27 @@ namespace snfft {
 // ---------------------------------------------------------------------------
 // kernel classes: (id, dmax, V columns per thread, W lanes, G row groups, RPT rows per thread,
 //                  NG column groups per CTA, NBUF chains per pass, MINB CTAs per SM wanted,
-//                  STAGE the task table in shared memory)
+//                  STAGE the task table in shared memory, RPTI rows per thread of the inverse kernel)
 // A shape of dimension d runs in the first class with dmax >= d.  The column
 // tile is TC = V * W slots; shared memory = NG * NBUF * d * TC * sizeof(T) + table.
+// The forward kernel keeps RPT * G >= d_lambda output rows in registers; the inverse kernel keeps the rows of
+// the child block, and the children of the shapes of one class are much smaller than dmax (n <= 12: at most
+// 35 / 90 / 216 / 768 / 2310 rows in classes 1..5), so RPTI * G only has to cover those (checked at launch).
 // ---------------------------------------------------------------------------
 #define SNFFT_CLASSES_F32(X)                                                                            \
-    X(0, 16, 1, 32, 1, 16, 8, 1, 4, true) X(1, 96, 4, 8, 16, 6, 1, 2, 6, true)                          \
-    X(2, 256, 4, 8, 32, 8, 1, 2, 3, true) X(3, 768, 4, 4, 128, 6, 1, 2, 2, true)                        \
-    X(4, 2310, 4, 2, 512, 5, 1, 2, 1, true) X(5, 7700, 4, 1, 1024, 8, 1, 1, 1, false)
+    X(0, 16, 1, 32, 1, 16, 8, 1, 4, true, 16) X(1, 96, 4, 8, 16, 6, 1, 2, 6, true, 3)                   \
+    X(2, 256, 4, 8, 32, 8, 1, 2, 3, true, 3) X(3, 768, 4, 4, 64, 12, 1, 2, 2, true, 4)                  \
+    X(4, 2310, 4, 2, 512, 5, 1, 2, 1, true, 2) X(5, 7700, 4, 1, 1024, 8, 1, 1, 1, false, 3)
 #define SNFFT_CLASSES_F64(X)                                                                            \
-    X(0, 16, 1, 32, 1, 16, 8, 1, 4, true) X(1, 96, 2, 8, 16, 6, 1, 2, 6, true)                          \
-    X(2, 256, 2, 8, 32, 8, 1, 2, 3, true) X(3, 768, 2, 4, 128, 6, 1, 2, 2, true)                        \
-    X(4, 2310, 2, 2, 512, 5, 1, 2, 1, true) X(5, 7700, 2, 1, 1024, 8, 1, 1, 1, false)
+    X(0, 16, 1, 32, 1, 16, 8, 1, 4, true, 16) X(1, 96, 2, 8, 16, 6, 1, 2, 6, true, 3)                   \
+    X(2, 256, 2, 8, 32, 8, 1, 2, 3, true, 3) X(3, 768, 2, 4, 128, 6, 1, 2, 2, true, 2)                  \
+    X(4, 2310, 2, 2, 512, 5, 1, 2, 1, true, 2) X(5, 7700, 2, 1, 1024, 8, 1, 1, 1, false, 3)
 
 struct KClass {
     int id, dmax, V, W, G, RPT, NG, NBUF, MINB;
     bool STAGE;
 };
-#define SNFFT_ROW(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE) {id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE},
+#define SNFFT_ROW(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE, RPTI) {id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE},
 static const KClass kClasses32[] = {SNFFT_CLASSES_F32(SNFFT_ROW)};
 static const KClass kClasses64[] = {SNFFT_CLASSES_F64(SNFFT_ROW)};
 static const int kNumClasses = 6;
@@ -453,7 +456,7 @@ static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, 
         ProfScope prof(p, st, 0, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
             switch (r.cls) {
-#define SNFFT_CASE(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE) \
+#define SNFFT_CASE(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE, RPTI) \
     case id: rc = launch_fwd_range<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>(r, a, st); break;
                 SNFFT_CLASSES_F32(SNFFT_CASE)
             }
@@ -474,8 +477,11 @@ static int run_inv_level(const snfft_plan* p, int k, const void* in, void* out, 
         ProfScope prof(p, st, 1, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
             switch (r.cls) {
-#define SNFFT_CASE(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE) \
-    case id: rc = launch_inv_range<T, V, W, G, RPT, NG, NBUF, MINB, STAGE>(r, a, st); break;
+#define SNFFT_CASE(id, dmax, V, W, G, RPT, NG, NBUF, MINB, STAGE, RPTI)                                   \
+    case id:                                                                                             \
+        if (r.max_dmu > RPTI * G) return set_error(SNFFT_ENOTSUP, "child block larger than the inverse class allows"); \
+        rc = launch_inv_range<T, V, W, G, RPTI, NG, NBUF, MINB, STAGE>(r, a, st);                        \
+        break;
                 SNFFT_CLASSES_F32(SNFFT_CASE)
             }
         } else {
