@@ -58,8 +58,8 @@ namespace snfft {
     X(2, 256, 4, 8, 16, 16, 1, 2, 3, true, 6) X(3, 768, 4, 4, 64, 12, 1, 2, 2, true, 4)                  \
     X(4, 2310, 4, 2, 512, 5, 1, 2, 1, true, 2) X(5, 7700, 4, 1, 1024, 8, 1, 1, 1, false, 3)
 #define SNFFT_CLASSES_F64(X)                                                                            \
-    X(0, 16, 1, 32, 1, 16, 8, 1, 4, true, 16) X(1, 96, 2, 8, 16, 6, 1, 2, 6, true, 3)                   \
-    X(2, 256, 2, 8, 32, 8, 1, 2, 3, true, 3) X(3, 768, 2, 4, 64, 12, 1, 2, 2, true, 4)                  \
+    X(0, 16, 1, 32, 1, 16, 8, 1, 4, true, 16) X(1, 96, 2, 8, 8, 12, 1, 2, 8, true, 5)                   \
+    X(2, 256, 2, 8, 16, 16, 1, 2, 3, true, 6) X(3, 768, 2, 4, 64, 12, 1, 2, 2, true, 4)                  \
     X(4, 2310, 2, 2, 512, 5, 1, 2, 1, true, 2) X(5, 7700, 2, 1, 1024, 8, 1, 1, 1, false, 3)
 
 struct KClass {

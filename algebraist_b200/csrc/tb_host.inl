@@ -63,8 +63,8 @@ static int tb_pick_s(int k) {
 }
 
 // Directions that use the TB kernels at level k.  Forced modes use them everywhere; the automatic
-// choice follows the measurements in profiles/ (r01f): for fp32 they win the forward steps k <= 9 and the
-// inverse step k = 7 (fp64: forward k = 7, 9, inverse k = 7); the sweep kernels run the rest.  SNFFT_TB_FWD / SNFFT_TB_INV (lists of levels, e.g.
+// choice follows the measurements in profiles/ (r01j): for fp32 they win the forward steps k = 7, 9 and the
+// inverse step k = 7 (fp64: forward k = 9); the sweep kernels run the rest.  SNFFT_TB_FWD / SNFFT_TB_INV (lists of levels, e.g.
 // "7,8,9") override the automatic choice when a plan is created (tuning only).
 static bool tb_level_listed(const char* env, int k, bool dflt) {
     const char* e = std::getenv(env);
@@ -83,8 +83,8 @@ static void tb_pick_dirs(int k, int dtype, bool* fwd, bool* inv) {
         *fwd = *inv = true;
         return;
     }
-    *fwd = tb_level_listed("SNFFT_TB_FWD", k, dtype == SNFFT_F32 ? k <= 9 : (k == 7 || k == 9));
-    *inv = tb_level_listed("SNFFT_TB_INV", k, k == 7);
+    *fwd = tb_level_listed("SNFFT_TB_FWD", k, dtype == SNFFT_F32 ? (k == 7 || k == 9) : k == 9);
+    *inv = tb_level_listed("SNFFT_TB_INV", k, dtype == SNFFT_F32 && k == 7);
 }
 
 struct TbPath {
