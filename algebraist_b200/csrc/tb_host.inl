@@ -39,6 +39,12 @@ static size_t tb_smem_cap(int nt) {
     return (sizeof(T) == 4 && nt == 256) ? TB_SMEM_CAP_2 : TB_SMEM_CAP_1;
 }
 static int tb_pad4(int x) { return (x + 3) & ~3; }
+// tuning switch: SNFFT_TB_TCMAX = log2 of the widest column-instance tile the TB kernels may use (default 7)
+static int tb_tcl_max() {
+    const char* e = std::getenv("SNFFT_TB_TCMAX");
+    const int v = e ? std::atoi(e) : 7;
+    return v < 2 ? 2 : (v > 7 ? 7 : v);
+}
 
 static bool tb_combo_compiled(int mb, int s) {
 #define SNFFT_TB_HAS(MB, S, MAXIN) \
@@ -281,7 +287,7 @@ static int build_tb_level(snfft_plan* p, int k, int s) {
             bt.resize(tb_pad4((int)bt.size()), 0u);
             tk.bt_words = (int)(bt.size() - (size_t)tk.bt_off);
             // tile width: the largest whose B role fits a CTA and whose buffers fit shared memory
-            int tcl = 7, nt = 0;
+            int tcl = tb_tcl_max(), nt = 0;
             for (; tcl >= vtl; --tcl) {
                 nt = tb_pick_nt<T>((long long)nsb << tcl);
                 if (nt && tb_smem_bytes<T>(false, TB_NBUF, S.dim << tcl, M.dim << tcl, tk.ct_len, tk.tt_words, tk.bt_words) <=
@@ -346,7 +352,7 @@ static int build_tb_level(snfft_plan* p, int k, int s) {
             mbt = std::max(mbt, t.bt_words);
             tasks.push_back(t);
         }
-        int tcl = 7, nt = 0;
+        int tcl = tb_tcl_max(), nt = 0;
         for (; tcl >= vtl; --tcl) {
             nt = tb_pick_nt<T>(std::max((long long)maxnsb << tcl, (long long)it.R << (tcl - vtl)));
             if (nt && tb_smem_bytes<T>(true, tb_inv_nbuf(k, s), maxd << tcl, 0, mct, mtt, mbt) <= tb_smem_cap<T>(nt)) break;
