@@ -1,32 +1,51 @@
 """Build the C-ABI library `libsnfft_b200.so` in-tree with nvcc for sm_100a.
 
-    python -m algebraist_b200._build
+    python -m algebraist_b200._build [--force] [-v]
 
-The .so is git-ignored but travels to the GPU box with the repository
-snapshot.  There is no CPU build of the product: if nvcc is missing this
-raises."""
+The generated column kernels (csrc/col_tu.cu) are compiled as one translation unit per
+(level, dtype, direction), in parallel with the main one; objects are cached under `_obj/`.
+The .so is git-ignored but travels to the GPU box with the repository snapshot.  There is no
+CPU build of the product: if nvcc is missing this raises."""
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", "snfft.cu"), os.path.join(HERE, "csrc", "plan.cpp")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "plan.h", "level_tb.cuh", "bot_gen.cuh", "base_gen.cuh", "tb_host.inl")] + [
-    os.path.join(HERE, "..", "include", "snfft.h")]
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libsnfft_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "snfft.h")
 
-NVCC_FLAGS = [
-    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
-]
+MAIN_DEPS = [os.path.join(CSRC, f) for f in ("snfft.cu", "kernels.cuh", "plan.h", "level_tb.cuh", "bot_gen.cuh",
+                                             "base_gen.cuh", "tb_host.inl")] + [HEADER]
+PLAN_DEPS = [os.path.join(CSRC, f) for f in ("plan.cpp", "plan.h")]
+COL_DEPS = [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", "col_gen.cuh")]
+COL_COMBOS = [(k, f64, inv) for k in (7, 8) for f64 in (0, 1) for inv in (0, 1)]
+
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+
+
+def units():
+    """(object, source, extra flags, dependencies); the largest translation units first."""
+    u = [(os.path.join(OBJ, f"col_{k}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "col_tu.cu"),
+          [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}"], COL_DEPS)
+         for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
+    u.insert(0, (os.path.join(OBJ, "snfft.o"), os.path.join(CSRC, "snfft.cu"), [], MAIN_DEPS))
+    u.append((os.path.join(OBJ, "plan.o"), os.path.join(CSRC, "plan.cpp"), [], PLAN_DEPS))
+    return u
+
+
+def stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def needs_build() -> bool:
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    return any(stale(o, d) for o, _, _, d in units()) or stale(OUT, [o for o, _, _, _ in units()])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -35,12 +54,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: the sm_100a library cannot be built")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    todo = [u for u in units() if force or stale(u[0], u[3])]
+
+    def compile_one(u):
+        obj, src, extra, _ = u
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + extra + ["-c", "-o", obj, src]
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+        for obj, res in ex.map(compile_one, todo):
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {os.path.basename(obj)}:\n" + res.stdout + res.stderr)
+            if verbose:
+                sys.stderr.write(res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + [u[0] for u in units()],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return OUT
 
 

@@ -1,0 +1,44 @@
+// One translation unit per (level, dtype, direction) of the column kernels (col_kernels.cuh): the generated
+// code is large, so the build compiles the eight combinations in parallel.
+//   -DSNFFT_COL_K=7|8  -DSNFFT_COL_F64=0|1  -DSNFFT_COL_INV=0|1
+// Exports  int snfft_col_launch_<K>_<f32|f64>_<fwd|inv>(in, out, ninst, stream)  (0 or a cudaError_t).
+#ifdef SNFFT_HOST_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+#include <cstdlib>
+
+#include "col_kernels.cuh"
+
+#if SNFFT_COL_F64
+typedef double col_t;
+#define COL_DT f64
+#else
+typedef float col_t;
+#define COL_DT f32
+#endif
+#if SNFFT_COL_INV
+#define COL_DIR inv
+#else
+#define COL_DIR fwd
+#endif
+#define COL_CAT_(k, dt, dir) snfft_col_launch_##k##_##dt##_##dir
+#define COL_CAT(k, dt, dir) COL_CAT_(k, dt, dir)
+
+extern "C" int COL_CAT(SNFFT_COL_K, COL_DT, COL_DIR)(const void* in, void* out, long long ninst, cudaStream_t st) {
+    using namespace snfft;
+    static const int chunk = [] {
+        const char* e = std::getenv("SNFFT_COL_CHUNK");       // tuning switch
+        return e ? std::atoi(e) : 148;
+    }();
+    const ColGroups g = col_groups<SNFFT_COL_K, SNFFT_COL_INV != 0>(ninst, chunk);
+    const unsigned nblk = g.blk0[g.ngroups];
+    if (nblk == 0) return 0;
+    dim3 grid(nblk, 1, 1), block(COL_THREADS, 1, 1);
+    auto kfn = col_kernel<col_t, SNFFT_COL_K, SNFFT_COL_INV != 0>;
+    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const col_t*)in, (col_t*)out, ninst, g);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,233 @@
+#!/usr/bin/env python
+"""Generate col_gen.cuh: register "column" code for the level steps k = 7 and k = 8.
+
+    python algebraist_b200/csrc/gen_col.py        # rewrites col_gen.cuh next to this file
+
+A level step (reference fourier.py:253-273, inverse formula fourier.py:191-199) treats every column of
+a block independently, and for k <= 8 the pieces of a column that the bottom sweeps keep together are
+small (d <= 35), so one thread can own them in registers and the Young's-orthogonal-form coefficients
+(irreps.py:91-109) become FFMA immediates -- no shared memory, no barriers, no tables:
+
+  forward task (lambda, child block b, row set R)  ->  rows R of  F_lambda[:, boff_b + c]
+       = sum_i rho(s_i) .. rho(s_{k-2}) embed_b(F^(i)_mu[:, c])           restricted to R
+  inverse task (mu, row set R)                     ->  rows R of  G^(i)_mu[:, c],  i = 0 .. k-1
+       = sum_lambda d_lambda/(k d_mu) [rho(s_{k-2}) .. rho(s_i) F_lambda[:, boff + c]]_{block mu}
+
+with c a run-time column and R all rows (k = 7) or one child block of the output (k = 8: the bottom sweeps
+s_0..s_{k-3} never leave such a block, only the top sweep s_{k-2} couples two of them).  Rows that are still
+zero (forward) or no longer needed (inverse) are dropped sweep by sweep, so the code has exactly the
+support-restricted operation count of the table-driven kernels.
+
+A thread is (task, column c, instance); the tasks that read the same child block mu form a group and run
+side by side so that their re-reads hit in L1 / L2.
+
+Generated per (K, direction):  ColInfo<K, INV> (groups for the host), col_run<T, K, INV>(task, c, in, out, s).
+Combinatorics come from gen_base.py (same conventions, same citations).
+"""
+import math
+import os
+
+from gen_base import Emitter, boffs, children, coef_off, dim, partitions, table
+
+LEVELS = (7, 8)
+
+
+def partner_checked(part, j, t):
+    q, dist = table(part, j)[t]
+    if q != t:
+        q2, dist2 = table(part, j)[q]
+        assert q2 == t and dist2 == -dist
+    return q, dist
+
+
+def sweep_need(em, part, j, x, need):
+    """x (dict row -> value) after rho_part(s_j), only on the rows in `need`."""
+    new = {}
+    for t in sorted(need):
+        q, dist = partner_checked(part, j, t)
+        if q == t:
+            v = x.get(t)
+            if v is not None:
+                new[t] = v if dist == 1 else (-v[0], v[1])
+            continue
+        a = 1.0 / dist
+        b = math.sqrt(1.0 - 1.0 / (dist * dist))
+        v = em.lin([(a, x.get(t)), (b, x.get(q))])
+        if v is not None:
+            new[t] = v
+    return new
+
+
+def need_chain(part, seq, rows):
+    """need[m] = rows that must be known after the first m sweeps of `seq` to get `rows` at the end."""
+    need = [None] * (len(seq) + 1)
+    need[-1] = set(rows)
+    for m in range(len(seq) - 1, -1, -1):
+        need[m] = set(need[m + 1])
+        for t in need[m + 1]:
+            need[m].add(table(part, seq[m])[t][0])
+    return need
+
+
+def forward_task(em, k, lam, b, rows, load, store):
+    mu = children(lam)[b]
+    bo, dm = boffs(lam)[b], dim(mu)
+    acc = {t: None for t in rows}
+    for i in range(k):
+        seq = list(range(k - 2, i - 1, -1))
+        need = need_chain(lam, seq, rows)
+        x = {}
+        for r in range(dm):
+            if bo + r in need[0]:
+                x[bo + r] = (1.0, load(r, i))
+        for m, j in enumerate(seq):
+            x = sweep_need(em, lam, j, x, need[m + 1])
+        for t in rows:
+            if x.get(t) is not None:
+                acc[t] = em.lin([(1.0, acc[t]), (1.0, x[t])])
+        em.lines.append("    SNFFT_CODE_FENCE();")     # keeps the loads of the next chain below this one (register pressure)
+    for t in rows:
+        store(t, acc[t])
+
+
+def inverse_task(em, k, mu, i, rows, load, store):
+    dm = dim(mu)
+    acc = {r: None for r in rows}
+    for lam in partitions(k):
+        ch = children(lam)
+        if mu not in ch:
+            continue
+        b = ch.index(mu)
+        bo, dl = boffs(lam)[b], dim(lam)
+        seq = list(range(i, k - 1))
+        need = need_chain(lam, seq, [bo + r for r in rows])
+        x = {t: (1.0, load(lam, t, bo)) for t in sorted(need[0])}
+        for m, j in enumerate(seq):
+            x = sweep_need(em, lam, j, x, need[m + 1])
+        scale = dl / (k * dm)
+        for r in rows:
+            if x.get(bo + r) is not None:
+                acc[r] = em.lin([(1.0, acc[r]), (scale, x[bo + r])])
+        em.lines.append("    SNFFT_CODE_FENCE();")     # one parent's loads at a time
+    for r in rows:
+        store(r, acc[r])
+
+
+def value_expr(v):
+    if v is None:
+        return "T(0)"
+    return v[1] if v[0] == 1.0 else f"-{v[1]}"
+
+
+def row_sets(k, part):
+    """Row sets a task of level k owns inside a column of `part`: everything (k = 7) or one child block."""
+    d = dim(part)
+    if k <= 7:
+        return [list(range(d))]
+    return [list(range(o, o + dim(c))) for c, o in zip(children(part), boffs(part))]
+
+
+def gen_level(k, inverse):
+    """Returns (code, groups, number of tasks, statements)."""
+    tag = f"col{k}{'i' if inverse else 'f'}"
+    funcs, cases, groups = [], [], []
+    total = 0
+    task = 0
+    for mu in partitions(k - 1):
+        dm = dim(mu)
+        task0 = task
+        if not inverse:
+            for lam in partitions(k):
+                if mu not in children(lam):
+                    continue
+                b = children(lam).index(mu)
+                bo, dl = boffs(lam)[b], dim(lam)
+                for rows in row_sets(k, lam):
+                    em = Emitter()
+                    cache = {}
+
+                    def load(r, i, em=em, cache=cache, dm=dm):
+                        if (r, i) not in cache:
+                            cache[(r, i)] = em.tmp(f"in[(size_t){r * dm * k + i} * s]")
+                        return cache[(r, i)]
+
+                    def store(t, v, em=em, lam=lam, dl=dl, bo=bo):
+                        em.lines.append(f"    out[(size_t){coef_off(lam) + t * dl + bo} * s] = {value_expr(v)};")
+
+                    forward_task(em, k, lam, b, rows, load, store)
+                    total += em.n
+                    funcs.append("\n".join([
+                        "template <typename T>",
+                        f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, size_t s) {{"
+                        f"   // {lam} <- {mu}, rows {rows[0]}..{rows[-1]}"] + em.lines + ["}"]) + "\n")
+                    cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)({coef_off(mu)} + c) * {k} * s, out + (size_t)c * s, s); break;")
+                    task += 1
+        else:
+            # one task per (row set, coset i): a function that ran all k chains would keep the addresses of the rows of
+            # F_lambda (the same in every chain) live throughout and spill
+            for rows in row_sets(k, mu):
+                for i in range(k):
+                    em = Emitter()
+
+                    def load(lam, t, bo, em=em):
+                        return em.tmp(f"in[(size_t){coef_off(lam) + t * dim(lam) + bo} * s]")
+
+                    def store(r, v, em=em, i=i, dm=dm):
+                        em.lines.append(f"    out[(size_t){r * dm * k + i} * s] = {value_expr(v)};")
+
+                    inverse_task(em, k, mu, i, rows, load, store)
+                    total += em.n
+                    funcs.append("\n".join([
+                        "template <typename T>",
+                        f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, size_t s) {{"
+                        f"   // {mu}, rows {rows[0]}..{rows[-1]}, coset {i}"] + em.lines + ["}"]) + "\n")
+                    cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)c * s, out + (size_t)({coef_off(mu)} + c) * {k} * s, s); break;")
+                    task += 1
+        groups.append((dm, task0, task - task0))
+    inv = "true" if inverse else "false"
+    code = funcs
+    code.append("\n".join([
+        f"template <> struct ColInfo<{k}, {inv}> {{",
+        f"    static constexpr int ngroups = {len(groups)};",
+        f"    static constexpr int ntasks = {task};",
+        "    static const int* dmu() { static const int v[] = {" + ", ".join(str(g[0]) for g in groups) + "}; return v; }",
+        "    static const int* task0() { static const int v[] = {" + ", ".join(str(g[1]) for g in groups) + "}; return v; }",
+        "    static const int* ntask() { static const int v[] = {" + ", ".join(str(g[2]) for g in groups) + "}; return v; }",
+        "};"]) + "\n")
+    code.append("\n".join([
+        "template <typename T>",
+        f"__device__ __forceinline__ void {tag}_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, size_t s) {{",
+        "    switch (task) {"] + cases + ["        default: break;", "    }", "}"]) + "\n")
+    return "\n".join(code), groups, task, total
+
+
+def main():
+    here = os.path.dirname(os.path.abspath(__file__))
+    parts = ["// GENERATED by gen_col.py -- do not edit.  Register column code of the level steps k = 7, 8",
+             "// (see gen_col.py for the derivation and the reference citations).",
+             "#pragma once", "#include <stddef.h>", "",
+             "#ifndef SNFFT_CODE_FENCE",
+             "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")",
+             "#endif", "", "namespace snfft {", "",
+             "template <int K, bool INV> struct ColInfo;", ""]
+    stats = {}
+    for k in LEVELS:
+        for inverse in (False, True):
+            code, groups, ntask, n = gen_level(k, inverse)
+            stats[(k, inverse)] = (ntask, n)
+            parts.append(code)
+    parts.append("template <typename T, int K, bool INV>")
+    parts.append("__device__ __forceinline__ void col_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, size_t s) {")
+    for k in LEVELS:
+        parts.append(f"    if constexpr (K == {k} && !INV) col{k}f_run<T>(task, c, in, out, s);")
+        parts.append(f"    if constexpr (K == {k} && INV) col{k}i_run<T>(task, c, in, out, s);")
+    parts.append("}")
+    parts.append("")
+    parts.append("}  // namespace snfft")
+    with open(os.path.join(here, "col_gen.cuh"), "w") as fh:
+        fh.write("\n".join(parts) + "\n")
+    print("(level, inverse): (tasks, statements)", stats)
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,8 @@ struct TbRange {          // one launch of the TB kernels: tasks that share a ti
 };
 
 struct DevLevel {
+    // column kernels (col_kernels.cuh, levels 7 and 8): registers only; chosen when the plan is created
+    bool col_fwd = false, col_inv = false;
     // TB kernels (level_tb.cuh): tb_s = 0 means the level runs the sweep-per-pass kernels
     int tb_s = 0;
     int tb_inv_nbuf = 2;                      // chains per pass of the inverse TB kernel at this level
@@ -613,6 +615,42 @@ static int run_l6(const snfft_plan* p, const void* in, void* out, long long B, c
     return SNFFT_OK;
 }
 
+// Column kernels (col_kernels.cuh / col_tu.cu: one translation unit per level, dtype and direction).
+extern "C" {
+#define SNFFT_COL_DECL(k, dt) \
+    int snfft_col_launch_##k##_##dt##_fwd(const void*, void*, long long, cudaStream_t); \
+    int snfft_col_launch_##k##_##dt##_inv(const void*, void*, long long, cudaStream_t);
+SNFFT_COL_DECL(7, f32) SNFFT_COL_DECL(7, f64) SNFFT_COL_DECL(8, f32) SNFFT_COL_DECL(8, f64)
+#undef SNFFT_COL_DECL
+}
+constexpr int kColFirst = 7, kColLast = 8;
+
+// Levels that use the column kernels: automatic kernel choice only (the forced TB / sweep modes of
+// snfft_debug_tb_mode keep testing those families), SNFFT_COL_FWD / SNFFT_COL_INV (lists of levels) override.
+static void col_pick_dirs(int k, bool* fwd, bool* inv) {
+    *fwd = *inv = false;
+    if (k < kColFirst || k > kColLast || g_tb_mode.load() != -1) return;
+    *fwd = tb_level_listed("SNFFT_COL_FWD", k, true);
+    *inv = tb_level_listed("SNFFT_COL_INV", k, true);
+}
+
+template <typename T, bool INVERSE>
+static int run_col_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st) {
+    const long long ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
+    ProfScope prof(p, st, INVERSE ? 1 : 0, k, -3, p->host.factorial[k]);
+    int rc;
+    if (sizeof(T) == 4) {
+        if (k == 7) rc = INVERSE ? snfft_col_launch_7_f32_inv(in, out, ninst, st) : snfft_col_launch_7_f32_fwd(in, out, ninst, st);
+        else rc = INVERSE ? snfft_col_launch_8_f32_inv(in, out, ninst, st) : snfft_col_launch_8_f32_fwd(in, out, ninst, st);
+    } else {
+        if (k == 7) rc = INVERSE ? snfft_col_launch_7_f64_inv(in, out, ninst, st) : snfft_col_launch_7_f64_fwd(in, out, ninst, st);
+        else rc = INVERSE ? snfft_col_launch_8_f64_inv(in, out, ninst, st) : snfft_col_launch_8_f64_fwd(in, out, ninst, st);
+    }
+    g_launches.fetch_add(1);
+    if (rc) return set_error(SNFFT_ECUDA, std::string("column kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return SNFFT_OK;
+}
+
 static IndexArgs make_index_args(int n);
 
 // levels 1..n of the forward pipeline; *result points at X_n (instance fastest) inside the workspace
@@ -640,7 +678,8 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
         k_first = kBaseK0 + 1;
     }
     for (int k = k_first; k <= p->n; ++k) {
-        if (p->lev[k].tb_s > 0 && p->lev[k].tb_fwd) rc = run_tb_level<T, false>(p, k, cur, nxt, B, st);
+        if (base == 0 && p->lev[k].col_fwd) rc = run_col_level<T, false>(p, k, cur, nxt, B, st);
+        else if (p->lev[k].tb_s > 0 && p->lev[k].tb_fwd) rc = run_tb_level<T, false>(p, k, cur, nxt, B, st);
         else rc = run_fwd_level<T>(p, k, cur, nxt, B, st);
         if (rc) return rc;
         std::swap(cur, nxt);
@@ -704,7 +743,8 @@ static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f
     if (base == 0 && p->n > 5) k_last = p->n > 6 ? 7 : 6;
     else if (base == 2 && p->n > kBaseK0) k_last = kBaseK0 + 1;
     for (int k = p->n; k >= k_last; --k) {
-        if (p->lev[k].tb_s > 0 && p->lev[k].tb_inv) rc = run_tb_level<T, true>(p, k, cur, bufs[which], B, st);
+        if (base == 0 && p->lev[k].col_inv) rc = run_col_level<T, true>(p, k, cur, bufs[which], B, st);
+        else if (p->lev[k].tb_s > 0 && p->lev[k].tb_inv) rc = run_tb_level<T, true>(p, k, cur, bufs[which], B, st);
         else rc = run_inv_level<T>(p, k, cur, bufs[which], B, st);
         if (rc) return rc;
         cur = bufs[which];
@@ -869,6 +909,7 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
         }
         for (int k = 2; k <= n; ++k) {
             int rc = dtype == SNFFT_F32 ? build_level<float>(p, k) : build_level<double>(p, k);
+            col_pick_dirs(k, &p->lev[k].col_fwd, &p->lev[k].col_inv);
             const int s = tb_pick_s(k);
             if (!rc && s > 0 && k - s >= 3) {
                 rc = dtype == SNFFT_F32 ? build_tb_level<float>(p, k, s) : build_tb_level<double>(p, k, s);

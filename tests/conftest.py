@@ -36,17 +36,26 @@ def load_transform_golden(n):
 
 
 def build_emu():
-    """g++ build of the CUDA sources against tests/emu/cuda_emu.h (tests only)."""
-    srcs = [os.path.join(CSRC, "snfft.cu"), os.path.join(CSRC, "plan.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h", "level_tb.cuh", "bot_gen.cuh",
-                                                   "base_gen.cuh", "tb_host.inl")] + [
-                   os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "snfft.h")]
-    if os.path.exists(EMU_SO) and all(os.path.getmtime(d) <= os.path.getmtime(EMU_SO) for d in deps):
-        return EMU_SO
-    os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O1", "-x", "c++", "-DSNFFT_HOST_EMU", "-I" + EMU_DIR, "-shared", "-fPIC",
-           "-o", EMU_SO] + srcs
-    subprocess.run(cmd, check=True)
+    """g++ build of the CUDA sources against tests/emu/cuda_emu.h (tests only).  Same translation units as the
+    product build (algebraist_b200/_build.py), objects cached under tests/emu/_build/."""
+    from concurrent.futures import ThreadPoolExecutor
+    from algebraist_b200 import _build as PB
+    bdir = os.path.dirname(EMU_SO)
+    os.makedirs(bdir, exist_ok=True)
+    emu_h = os.path.join(EMU_DIR, "cuda_emu.h")
+    units = [(os.path.join(bdir, os.path.basename(obj)), src, extra, deps + [emu_h]) for obj, src, extra, deps in PB.units()]
+    todo = [u for u in units if PB.stale(u[0], u[3])]
+
+    def compile_one(u):
+        obj, src, extra, _ = u
+        subprocess.run(["g++", "-std=c++17", "-O1", "-x", "c++", "-DSNFFT_HOST_EMU", "-I" + EMU_DIR, "-fPIC"] + extra +
+                       ["-c", "-o", obj, src], check=True)
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+            list(ex.map(compile_one, todo))
+    if todo or not os.path.exists(EMU_SO):
+        subprocess.run(["g++", "-shared", "-o", EMU_SO] + [u[0] for u in units], check=True)
     return EMU_SO
 
 

@@ -161,8 +161,10 @@ def test_launch_counter(emu):
 # (n, tb mode, base mode): which fused-top / register-bottom ("TB") kernel the level steps run.
 # mode -1 is the product's automatic choice, 0 the sweep-per-pass kernels, 1..3 force s fused top sweeps;
 # base 1 sends the levels <= 6 through the level kernels too, so small n reaches every (MB, s) combination.
-TB_CASES = [(7, -1, 0), (7, 2, 0), (7, 3, 0), (6, 1, 1), (6, 2, 1), (6, 3, 1), (5, 1, 1), (8, -1, 0), (8, 2, 0),
-            (8, 3, 0)]
+# Since the column kernels (col_kernels.cuh) own levels 7 and 8 in automatic mode, mode -1 at n = 7, 8 checks THEM
+# against the oracle and mode 1 keeps the TB kernels with one fused sweep covered.
+TB_CASES = [(7, -1, 0), (7, 1, 0), (7, 2, 0), (7, 3, 0), (6, 1, 1), (6, 2, 1), (6, 3, 1), (5, 1, 1), (8, -1, 0), (8, 1, 0),
+            (8, 2, 0), (8, 3, 0)]
 
 
 @pytest.mark.parametrize("n,mode,base", TB_CASES)
