@@ -21,8 +21,12 @@ HEADER = os.path.join(HERE, "..", "include", "snfft.h")
 MAIN_DEPS = [os.path.join(CSRC, f) for f in ("snfft.cu", "kernels.cuh", "plan.h", "level_tb.cuh", "bot_gen.cuh",
                                              "base_gen.cuh", "tb_host.inl")] + [HEADER]
 PLAN_DEPS = [os.path.join(CSRC, f) for f in ("plan.cpp", "plan.h")]
-COL_DEPS = [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", "col_gen.cuh")]
-COL_COMBOS = [(k, f64, inv) for k in (7, 8) for f64 in (0, 1) for inv in (0, 1)]
+def col_deps(k):
+    return [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", f"col_gen_{k}.cuh")]
+
+
+
+COL_COMBOS = [(k, f64, inv) for k in (6, 7, 8) for f64 in (0, 1) for inv in (0, 1)]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
@@ -30,7 +34,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 def units():
     """(object, source, extra flags, dependencies); the largest translation units first."""
     u = [(os.path.join(OBJ, f"col_{k}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "col_tu.cu"),
-          [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}"], COL_DEPS)
+          [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}"], col_deps(k))
          for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
     u.insert(0, (os.path.join(OBJ, "snfft.o"), os.path.join(CSRC, "snfft.cu"), [], MAIN_DEPS))
     u.append((os.path.join(OBJ, "plan.o"), os.path.join(CSRC, "plan.cpp"), [], PLAN_DEPS))

@@ -1,4 +1,4 @@
-// Column kernels for the level steps k = 7, 8 (generated code col_gen.cuh, gen_col.py).
+// Column kernels for the level steps k = 6, 7, 8 (generated code col_gen_<k>.cuh, gen_col.py).
 // A thread is (task, column c, instance): it owns the rows of one output column that the bottom sweeps keep
 // together (<= 35 values) in registers, reads its inputs straight from the level array below (lanes over
 // consecutive instances: every global access is a contiguous run) and writes its rows once.  Forward task:
@@ -13,7 +13,16 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#include "col_gen.cuh"
+#ifndef SNFFT_COL_K
+#error "col_kernels.cuh: define SNFFT_COL_K (6, 7 or 8) -- one translation unit per level"
+#endif
+#if SNFFT_COL_K == 6
+#include "col_gen_6.cuh"
+#elif SNFFT_COL_K == 7
+#include "col_gen_7.cuh"
+#elif SNFFT_COL_K == 8
+#include "col_gen_8.cuh"
+#endif
 
 namespace snfft {
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Generate col_gen.cuh: register "column" code for the level steps k = 7 and k = 8.
+"""Generate col_gen_<k>.cuh: register "column" code for the level steps k = 6, 7 and 8.
 
-    python algebraist_b200/csrc/gen_col.py        # rewrites col_gen.cuh next to this file
+    python algebraist_b200/csrc/gen_col.py        # rewrites col_gen_<k>.cuh next to this file
 
 A level step (reference fourier.py:253-273, inverse formula fourier.py:191-199) treats every column of
 a block independently, and for k <= 8 the pieces of a column that the bottom sweeps keep together are
@@ -13,7 +13,7 @@ small (d <= 35), so one thread can own them in registers and the Young's-orthogo
   inverse task (mu, row set R)                     ->  rows R of  G^(i)_mu[:, c],  i = 0 .. k-1
        = sum_lambda d_lambda/(k d_mu) [rho(s_{k-2}) .. rho(s_i) F_lambda[:, boff + c]]_{block mu}
 
-with c a run-time column and R all rows (k = 7) or one child block of the output (k = 8: the bottom sweeps
+with c a run-time column and R all rows (k <= 7) or one child block of the output (k = 8: the bottom sweeps
 s_0..s_{k-3} never leave such a block, only the top sweep s_{k-2} couples two of them).  Rows that are still
 zero (forward) or no longer needed (inverse) are dropped sweep by sweep, so the code has exactly the
 support-restricted operation count of the table-driven kernels.
@@ -29,7 +29,7 @@ import os
 
 from gen_base import Emitter, boffs, children, coef_off, dim, partitions, table
 
-LEVELS = (7, 8)
+LEVELS = (6, 7, 8)
 
 
 def partner_checked(part, j, t):
@@ -203,29 +203,29 @@ def gen_level(k, inverse):
 
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
-    parts = ["// GENERATED by gen_col.py -- do not edit.  Register column code of the level steps k = 7, 8",
-             "// (see gen_col.py for the derivation and the reference citations).",
-             "#pragma once", "#include <stddef.h>", "",
-             "#ifndef SNFFT_CODE_FENCE",
-             "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")",
-             "#endif", "", "namespace snfft {", "",
-             "template <int K, bool INV> struct ColInfo;", ""]
     stats = {}
-    for k in LEVELS:
+    for k in LEVELS:            # one header per level: a translation unit only sees (and depends on) its own
+        parts = [f"// GENERATED by gen_col.py -- do not edit.  Register column code of the level step k = {k}",
+                 "// (see gen_col.py for the derivation and the reference citations).",
+                 "#pragma once", "#include <stddef.h>", "",
+                 "#ifndef SNFFT_CODE_FENCE",
+                 "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")",
+                 "#endif", "", "namespace snfft {", "",
+                 "template <int K, bool INV> struct ColInfo;", ""]
         for inverse in (False, True):
             code, groups, ntask, n = gen_level(k, inverse)
             stats[(k, inverse)] = (ntask, n)
             parts.append(code)
-    parts.append("template <typename T, int K, bool INV>")
-    parts.append("__device__ __forceinline__ void col_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, size_t s) {")
-    for k in LEVELS:
-        parts.append(f"    if constexpr (K == {k} && !INV) col{k}f_run<T>(task, c, in, out, s);")
-        parts.append(f"    if constexpr (K == {k} && INV) col{k}i_run<T>(task, c, in, out, s);")
-    parts.append("}")
-    parts.append("")
-    parts.append("}  // namespace snfft")
-    with open(os.path.join(here, "col_gen.cuh"), "w") as fh:
-        fh.write("\n".join(parts) + "\n")
+        parts.append("template <typename T, int K, bool INV>")
+        parts.append("__device__ __forceinline__ void col_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, size_t s) {")
+        parts.append(f"    static_assert(K == {k}, \"this translation unit holds the code of one level\");")
+        parts.append(f"    if constexpr (!INV) col{k}f_run<T>(task, c, in, out, s);")
+        parts.append(f"    else col{k}i_run<T>(task, c, in, out, s);")
+        parts.append("}")
+        parts.append("")
+        parts.append("}  // namespace snfft")
+        with open(os.path.join(here, f"col_gen_{k}.cuh"), "w") as fh:
+            fh.write("\n".join(parts) + "\n")
     print("(level, inverse): (tasks, statements)", stats)
 
 

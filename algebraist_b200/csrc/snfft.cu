@@ -112,7 +112,7 @@ struct TbRange {          // one launch of the TB kernels: tasks that share a ti
 };
 
 struct DevLevel {
-    // column kernels (col_kernels.cuh, levels 7 and 8): registers only; chosen when the plan is created
+    // column kernels (col_kernels.cuh, levels 6..8): registers only; chosen when the plan is created
     bool col_fwd = false, col_inv = false;
     // TB kernels (level_tb.cuh): tb_s = 0 means the level runs the sweep-per-pass kernels
     int tb_s = 0;
@@ -620,10 +620,11 @@ extern "C" {
 #define SNFFT_COL_DECL(k, dt) \
     int snfft_col_launch_##k##_##dt##_fwd(const void*, void*, long long, cudaStream_t); \
     int snfft_col_launch_##k##_##dt##_inv(const void*, void*, long long, cudaStream_t);
-SNFFT_COL_DECL(7, f32) SNFFT_COL_DECL(7, f64) SNFFT_COL_DECL(8, f32) SNFFT_COL_DECL(8, f64)
+SNFFT_COL_DECL(6, f32) SNFFT_COL_DECL(6, f64) SNFFT_COL_DECL(7, f32) SNFFT_COL_DECL(7, f64) SNFFT_COL_DECL(8, f32)
+SNFFT_COL_DECL(8, f64)
 #undef SNFFT_COL_DECL
 }
-constexpr int kColFirst = 7, kColLast = 8;
+constexpr int kColFirst = 6, kColLast = 8;
 
 // Levels that use the column kernels: automatic kernel choice only (the forced TB / sweep modes of
 // snfft_debug_tb_mode keep testing those families), SNFFT_COL_FWD / SNFFT_COL_INV (lists of levels) override.
@@ -639,13 +640,10 @@ static int run_col_level(const snfft_plan* p, int k, const void* in, void* out, 
     const long long ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
     ProfScope prof(p, st, INVERSE ? 1 : 0, k, -3, p->host.factorial[k]);
     int rc;
-    if (sizeof(T) == 4) {
-        if (k == 7) rc = INVERSE ? snfft_col_launch_7_f32_inv(in, out, ninst, st) : snfft_col_launch_7_f32_fwd(in, out, ninst, st);
-        else rc = INVERSE ? snfft_col_launch_8_f32_inv(in, out, ninst, st) : snfft_col_launch_8_f32_fwd(in, out, ninst, st);
-    } else {
-        if (k == 7) rc = INVERSE ? snfft_col_launch_7_f64_inv(in, out, ninst, st) : snfft_col_launch_7_f64_fwd(in, out, ninst, st);
-        else rc = INVERSE ? snfft_col_launch_8_f64_inv(in, out, ninst, st) : snfft_col_launch_8_f64_fwd(in, out, ninst, st);
-    }
+#define SNFFT_COL_CALL(kk, dt) (INVERSE ? snfft_col_launch_##kk##_##dt##_inv(in, out, ninst, st) : snfft_col_launch_##kk##_##dt##_fwd(in, out, ninst, st))
+    if (sizeof(T) == 4) rc = k == 6 ? SNFFT_COL_CALL(6, f32) : (k == 7 ? SNFFT_COL_CALL(7, f32) : SNFFT_COL_CALL(8, f32));
+    else rc = k == 6 ? SNFFT_COL_CALL(6, f64) : (k == 7 ? SNFFT_COL_CALL(7, f64) : SNFFT_COL_CALL(8, f64));
+#undef SNFFT_COL_CALL
     g_launches.fetch_add(1);
     if (rc) return set_error(SNFFT_ECUDA, std::string("column kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     return SNFFT_OK;
@@ -668,7 +666,7 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
         std::swap(cur, nxt);
         k_first = 6;
         if (p->n > 6) {
-            if ((rc = run_l6<T, false>(p, cur, nxt, B, st))) return rc;
+            if ((rc = p->lev[6].col_fwd ? run_col_level<T, false>(p, 6, cur, nxt, B, st) : run_l6<T, false>(p, cur, nxt, B, st))) return rc;
             std::swap(cur, nxt);
             k_first = 7;
         }
@@ -752,7 +750,7 @@ static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f
     }
     if (base == 0 && p->n > 5) {
         if (p->n > 6) {
-            if ((rc = run_l6<T, true>(p, cur, bufs[which], B, st))) return rc;
+            if ((rc = p->lev[6].col_inv ? run_col_level<T, true>(p, 6, cur, bufs[which], B, st) : run_l6<T, true>(p, cur, bufs[which], B, st))) return rc;
             cur = bufs[which];
             which ^= 1;
         }

@@ -10,10 +10,57 @@ streams: chunk i+1 is copied in while chunk i is transformed and chunk i-1 is co
 `fn` is any function of a device tensor (rows = functions) that returns a device tensor with the same number of
 rows, e.g. a forward+inverse pair, a convolution through the transform, or a projection onto some partitions.
 """
+import os
+
 import torch
 
 
-def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, chunk: int = 32, device=None):
+def bind_host_to_device_node(device=None):
+    """Restrict this process to the CPUs of the NUMA node the GPU hangs off, so that host buffers allocated
+    (first touched) afterwards are local to the GPU's PCIe root: copies from the far socket run at about half the
+    bandwidth.  Call it before allocating the pinned buffers.  Returns the node, or None when the topology cannot
+    be read (then nothing is changed)."""
+    try:
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        pr = torch.cuda.get_device_properties(idx)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
+def chunk_schedule(batch: int, chunk: int, ramp: bool = True):
+    """Row counts of the chunks.  With `ramp` the first and the last chunks are short (chunk/4, chunk/2): the
+    pipeline cannot hide the copy-in of the first chunk nor the copy-out of the last one, so those are kept small
+    while the chunks in between stay large enough for the kernels to run at full efficiency."""
+    sizes = []
+    head = [c for c in (chunk // 4, chunk // 2) if c >= 1] if ramp else []
+    if batch < 2 * sum(head) + chunk:
+        head = []
+    tail = head[::-1]
+    left = batch - sum(head) - sum(tail)
+    sizes += head
+    while left > 0:
+        sizes.append(min(chunk, left))
+        left -= sizes[-1]
+    return sizes + tail
+
+
+def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, chunk: int = 32, device=None,
+                   ramp: bool = True):
     """Apply `fn` to the rows of `src_host` chunk by chunk on `device`, writing the results to `dst_host`.
 
     src_host : (B, ...) host tensor; pin it (`.pin_memory()`) or the copies cannot overlap anything.
@@ -40,30 +87,35 @@ def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, ch
     start = torch.cuda.Event()
     start.record(compute)
     s_in.wait_event(start)                             # src_host may have been produced by work queued on `compute`
-    nchunks = (batch + chunk - 1) // chunk
+    sizes = chunk_schedule(batch, chunk, ramp)
+    bounds = [0]
+    for m in sizes:
+        bounds.append(bounds[-1] + m)
+    nchunks = len(sizes)
+    cmax = max(sizes)
 
     def copy_in(c):
         s = c % nslots
-        lo, hi = c * chunk, min((c + 1) * chunk, batch)
+        lo, hi = bounds[c], bounds[c + 1]
         with torch.cuda.stream(s_in):
             if in_free[s] is not None:
                 s_in.wait_event(in_free[s])
-            if ins[s] is None or ins[s].shape[0] != hi - lo:
-                ins[s] = torch.empty((hi - lo,) + tuple(src_host.shape[1:]), dtype=src_host.dtype, device=dev)
-            ins[s].copy_(src_host[lo:hi], non_blocking=True)
+            if ins[s] is None:
+                ins[s] = torch.empty((cmax,) + tuple(src_host.shape[1:]), dtype=src_host.dtype, device=dev)
+            ins[s][:hi - lo].copy_(src_host[lo:hi], non_blocking=True)
             in_ready[s] = torch.cuda.Event()
             in_ready[s].record(s_in)
 
     copy_in(0)
     for c in range(nchunks):
         s = c % nslots
-        lo, hi = c * chunk, min((c + 1) * chunk, batch)
+        lo, hi = bounds[c], bounds[c + 1]
         if c + 1 < nchunks:
             copy_in(c + 1)                             # overlaps the transform of chunk c
         compute.wait_event(in_ready[s])
         if out_free[s] is not None:
             compute.wait_event(out_free[s])            # the previous result in this slot has left the device
-        res = fn(ins[s])
+        res = fn(ins[s][:hi - lo])
         outs[s] = res                                  # keeps the result alive until its copy has been queued
         in_free[s] = torch.cuda.Event()
         in_free[s].record(compute)

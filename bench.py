@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=128, help="functions per GPU")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=0, help="functions per chunk of the end-to-end pipeline (0 = batch / 16)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the process to the GPU's NUMA node for the e2e leg")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="functions per chunk of the end-to-end pipeline (0 = batch / 8)")
     ap.add_argument("--workload", default="batch", choices=["batch", "coset"],
                     help="batch: BASELINE configs 2-4 (default); coset: config 5, ONE S_n function (default n = 11) sharded "
                          "over the top-level cosets with a reduce-scatter by partition (torchrun, N >= 2)")
@@ -258,31 +259,36 @@ def run_native(a):
     ms = t.item()
     value = world * B * a.steps / (ms / 1000.0)
 
-    # end to end through the public Python API with host buffers
+    # end to end through the public Python API with host buffers (allocated on the GPU's NUMA node)
+    from algebraist_b200 import stream_batches
+    from algebraist_b200.host_pipeline import bind_host_to_device_node
+    affinity0 = os.sched_getaffinity(0)
+    numa_node = None if a.no_numa_bind else bind_host_to_device_node(dev)
     f_host = torch.randn(B, nf, dtype=tdt).pin_memory()
     out_host = torch.empty(B, nf, dtype=tdt).pin_memory()
-
-    from algebraist_b200 import stream_batches
-    e2e_chunk = a.e2e_chunk if a.e2e_chunk > 0 else max(4, B // 16)
+    e2e_chunk = a.e2e_chunk if a.e2e_chunk > 0 else max(4, B // 8)
 
     def e2e_step():
         # public API for host-resident batches: chunks of the batch stream through the GPU, the copies of
         # chunk i+1 / i-1 overlap the transform of chunk i (all of them are inside the timed region)
         stream_batches(lambda x: sn_ifft(sn_fft(x, n), n), f_host, out_host, chunk=e2e_chunk, device=dev)
 
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(a.steps, 5))
+    e2e_steps = max(2, min(a.steps, 20))
+    e2e_marks = [t0]
     for _ in range(e2e_steps):
-        e2e_step()
+        e2e_step()                      # returns when the last result is in host memory
+        e2e_marks.append(time.perf_counter())
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / e2e_s.item()
     e2e_err = ((out_host - f_host).double().norm() / f_host.double().norm()).item()
+    os.sched_setaffinity(0, affinity0)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -321,7 +327,9 @@ def run_native(a):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * nf * esize,
                     "d2h_bytes_per_step": B * nf * esize, "steps": e2e_steps, "round_trip_rel_err": e2e_err,
-                    "path": f"pinned host -> stream_batches(sn_ifft(sn_fft(.)), chunk={e2e_chunk}) -> pinned host "
+                    "ms_per_step_each": [round((y - x) * 1e3, 2) for x, y in zip(e2e_marks, e2e_marks[1:])],
+                    "host_numa_node": numa_node,
+                    "path": f"pinned host -> stream_batches(sn_ifft(sn_fft(.)), chunk={e2e_chunk}, short first/last chunks) -> pinned host "
                             "(H2D, kernels and D2H of consecutive chunks overlap on three streams)"},
         }
         if world == 1 and not a.no_cpu_baseline:
