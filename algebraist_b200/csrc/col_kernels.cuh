@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(COL_THREADS, sizeof(T) == 4 ? 5 : 3) col_kerne
     if (q >= qn) return;
     const int c = (int)(q / ninst);
     const long long inst = q - (long long)c * ninst;
-    col_run<T, K, INV>(task, c, in + inst, out + inst, (size_t)ninst);
+    // 32-bit row stride: every element address is ONE wide multiply-add (stride * constant + base)
+    col_run<T, K, INV>(task, c, in + inst, out + inst, (unsigned)ninst);
 }
 
 }  // namespace snfft

@@ -37,6 +37,7 @@ extern "C" int COL_CAT(SNFFT_COL_K, COL_DT, COL_DIR)(const void* in, void* out, 
     const ColGroups g = col_groups<SNFFT_COL_K, SNFFT_COL_INV != 0>(ninst, chunk);
     const unsigned nblk = g.blk0[g.ngroups];
     if (nblk == 0) return 0;
+    if (ninst >= (1ll << 32)) return (int)cudaErrorInvalidValue;     // the kernels use a 32-bit row stride
     dim3 grid(nblk, 1, 1), block(COL_THREADS, 1, 1);
     auto kfn = col_kernel<col_t, SNFFT_COL_K, SNFFT_COL_INV != 0>;
     SNFFT_LAUNCH(kfn, grid, block, 0, st, (const col_t*)in, (col_t*)out, ninst, g);

@@ -30,6 +30,7 @@ import os
 from gen_base import Emitter, boffs, children, coef_off, dim, partitions, table
 
 LEVELS = (6, 7, 8)
+CHILD_MAJOR_MAX = 6       # levels whose tasks keep a whole child column in registers
 
 
 def partner_checked(part, j, t):
@@ -90,7 +91,18 @@ def forward_task(em, k, lam, b, rows, load, store):
         store(t, acc[t])
 
 
+def block_of(lam, t):
+    """Index of the child block of `lam` that row t lies in."""
+    for b, (c, o) in enumerate(zip(children(lam), boffs(lam))):
+        if o <= t < o + dim(c):
+            return b
+    raise ValueError(t)
+
+
 def inverse_task(em, k, mu, i, rows, load, store):
+    """Rows `rows` of G^(i)_mu[:, c].  The bottom sweeps s_i..s_{k-3} never leave a child block of lambda, so the
+    column of F_lambda is processed one child block at a time (loads, bottom sweeps, its term of the top sweep
+    s_{k-2} added to the running sums): only the sums and one block are live at any point."""
     dm = dim(mu)
     acc = {r: None for r in rows}
     for lam in partitions(k):
@@ -99,16 +111,36 @@ def inverse_task(em, k, mu, i, rows, load, store):
             continue
         b = ch.index(mu)
         bo, dl = boffs(lam)[b], dim(lam)
-        seq = list(range(i, k - 1))
-        need = need_chain(lam, seq, [bo + r for r in rows])
-        x = {t: (1.0, load(lam, t, bo)) for t in sorted(need[0])}
-        for m, j in enumerate(seq):
-            x = sweep_need(em, lam, j, x, need[m + 1])
         scale = dl / (k * dm)
-        for r in rows:
-            if x.get(bo + r) is not None:
-                acc[r] = em.lin([(1.0, acc[r]), (scale, x[bo + r])])
-        em.lines.append("    SNFFT_CODE_FENCE();")     # one parent's loads at a time
+        want = [bo + r for r in rows]
+        if i > k - 2:                       # coset k-1: identity
+            for r in rows:
+                acc[r] = em.lin([(1.0, acc[r]), (scale, (1.0, load(lam, bo + r, bo)))])
+            em.lines.append("    SNFFT_CODE_FENCE();")
+            continue
+        # top sweep s_{k-2} (applied last): out[t] = a_t y[t] + b_t y[q_t], y = rows after the bottom sweeps
+        top = {}
+        for t in want:
+            q, dist = partner_checked(lam, k - 2, t)
+            if q == t:
+                top[t] = [(float(dist), t)]
+            else:
+                top[t] = [(1.0 / dist, t), (math.sqrt(1.0 - 1.0 / (dist * dist)), q)]
+        by_block = {}
+        for t in want:
+            for coef, src in top[t]:
+                by_block.setdefault(block_of(lam, src), []).append((t, coef, src))
+        seq = list(range(i, k - 2))         # bottom sweeps, ascending
+        for blk in sorted(by_block, key=lambda x: (x != b, x)):       # the block of mu first
+            terms = by_block[blk]
+            need = need_chain(lam, seq, sorted({src for _, _, src in terms}))
+            x = {t: (1.0, load(lam, t, bo)) for t in sorted(need[0])}
+            for m, j in enumerate(seq):
+                x = sweep_need(em, lam, j, x, need[m + 1])
+            for t, coef, src in terms:
+                if x.get(src) is not None:
+                    acc[t - bo] = em.lin([(1.0, acc[t - bo]), (scale * coef, x[src])])
+            em.lines.append("    SNFFT_CODE_FENCE();")     # one block's loads at a time
     for r in rows:
         store(r, acc[r])
 
@@ -136,7 +168,66 @@ def gen_level(k, inverse):
     for mu in partitions(k - 1):
         dm = dim(mu)
         task0 = task
-        if not inverse:
+        if not inverse and k <= CHILD_MAJOR_MAX:
+            # child-major: one task per mu; the k * d_mu inputs of the column are loaded once and stay in registers
+            # for every parent lambda (k * d_mu <= 36 values at k = 6)
+            em = Emitter()
+            cache = {}
+
+            def load(r, i, em=em, cache=cache, dm=dm):
+                if (r, i) not in cache:
+                    cache[(r, i)] = em.tmp(f"in[(size_t){r * dm * k + i} * s]")
+                return cache[(r, i)]
+
+            for r in range(dm):                 # every load first (memory-level parallelism)
+                for i in range(k):
+                    load(r, i)
+            for lam in partitions(k):
+                if mu not in children(lam):
+                    continue
+                b = children(lam).index(mu)
+                bo, dl = boffs(lam)[b], dim(lam)
+
+                def store(t, v, em=em, lam=lam, dl=dl, bo=bo):
+                    em.lines.append(f"    out[(size_t){coef_off(lam) + t * dl + bo} * s] = {value_expr(v)};")
+
+                forward_task(em, k, lam, b, list(range(dl)), load, store)
+            total += em.n
+            funcs.append("\n".join([
+                "template <typename T>",
+                f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned s) {{"
+                f"   // all parents of {mu}"] + em.lines + ["}"]) + "\n")
+            cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)({coef_off(mu)} + c) * {k} * s, out + (size_t)c * s, s); break;")
+            task += 1
+        elif inverse and k <= CHILD_MAJOR_MAX:
+            # one task per mu: the columns of the parents (sum of d_lambda = k * d_mu values) are loaded once and
+            # shared by the k cosets
+            em = Emitter()
+            cache = {}
+
+            def load(lam, t, bo, em=em, cache=cache):
+                if (lam, t) not in cache:
+                    cache[(lam, t)] = em.tmp(f"in[(size_t){coef_off(lam) + t * dim(lam) + bo} * s]")
+                return cache[(lam, t)]
+
+            for lam in partitions(k):
+                if mu in children(lam):
+                    bo = boffs(lam)[children(lam).index(mu)]
+                    for t in range(dim(lam)):
+                        load(lam, t, bo)
+            for i in range(k):
+                def store(r, v, em=em, i=i, dm=dm):
+                    em.lines.append(f"    out[(size_t){r * dm * k + i} * s] = {value_expr(v)};")
+
+                inverse_task(em, k, mu, i, list(range(dm)), load, store)
+            total += em.n
+            funcs.append("\n".join([
+                "template <typename T>",
+                f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned s) {{"
+                f"   // {mu}, every coset"] + em.lines + ["}"]) + "\n")
+            cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)c * s, out + (size_t)({coef_off(mu)} + c) * {k} * s, s); break;")
+            task += 1
+        elif not inverse:
             for lam in partitions(k):
                 if mu not in children(lam):
                     continue
@@ -158,14 +249,14 @@ def gen_level(k, inverse):
                     total += em.n
                     funcs.append("\n".join([
                         "template <typename T>",
-                        f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, size_t s) {{"
+                        f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned s) {{"
                         f"   // {lam} <- {mu}, rows {rows[0]}..{rows[-1]}"] + em.lines + ["}"]) + "\n")
                     cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)({coef_off(mu)} + c) * {k} * s, out + (size_t)c * s, s); break;")
                     task += 1
         else:
             # one task per (row set, coset i): a function that ran all k chains would keep the addresses of the rows of
             # F_lambda (the same in every chain) live throughout and spill
-            for rows in row_sets(k, mu):
+            for rows in row_sets(7, mu):                 # all rows of mu: the block of mu in F_lambda is then read once
                 for i in range(k):
                     em = Emitter()
 
@@ -179,7 +270,7 @@ def gen_level(k, inverse):
                     total += em.n
                     funcs.append("\n".join([
                         "template <typename T>",
-                        f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, size_t s) {{"
+                        f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned s) {{"
                         f"   // {mu}, rows {rows[0]}..{rows[-1]}, coset {i}"] + em.lines + ["}"]) + "\n")
                     cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)c * s, out + (size_t)({coef_off(mu)} + c) * {k} * s, s); break;")
                     task += 1
@@ -196,7 +287,7 @@ def gen_level(k, inverse):
         "};"]) + "\n")
     code.append("\n".join([
         "template <typename T>",
-        f"__device__ __forceinline__ void {tag}_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, size_t s) {{",
+        f"__device__ __forceinline__ void {tag}_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, unsigned s) {{",
         "    switch (task) {"] + cases + ["        default: break;", "    }", "}"]) + "\n")
     return "\n".join(code), groups, task, total
 
@@ -217,15 +308,17 @@ def main():
             stats[(k, inverse)] = (ntask, n)
             parts.append(code)
         parts.append("template <typename T, int K, bool INV>")
-        parts.append("__device__ __forceinline__ void col_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, size_t s) {")
+        parts.append("__device__ __forceinline__ void col_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, unsigned s) {")
         parts.append(f"    static_assert(K == {k}, \"this translation unit holds the code of one level\");")
         parts.append(f"    if constexpr (!INV) col{k}f_run<T>(task, c, in, out, s);")
         parts.append(f"    else col{k}i_run<T>(task, c, in, out, s);")
         parts.append("}")
         parts.append("")
         parts.append("}  // namespace snfft")
-        with open(os.path.join(here, f"col_gen_{k}.cuh"), "w") as fh:
-            fh.write("\n".join(parts) + "\n")
+        path, text = os.path.join(here, f"col_gen_{k}.cuh"), "\n".join(parts) + "\n"
+        if not os.path.exists(path) or open(path).read() != text:      # untouched levels keep their objects
+            with open(path, "w") as fh:
+                fh.write(text)
     print("(level, inverse): (tasks, statements)", stats)
 
 

@@ -24,13 +24,13 @@ def main():
     ki, ti, ri, wi = h.index("kernel"), h.index("time"), h.index("dram_rd"), h.index("dram_wr")
     recs = []
     # dominant kernels of the bench line: the largest launch of each sweep-kernel class, by family
-    fam = {"inv_level_kernel<float, 4, 4, 128": "inv_level_k10_c3", "fwd_level_kernel<float, 4, 4, 128": "fwd_level_k10_c3",
-           "inv_level_kernel<double, 2, 4, 128": "inv_level_k10_c3", "fwd_level_kernel<double, 2, 4, 128": "fwd_level_k10_c3"}
+    fam = {"inv_level_kernel<float, 4, 4, 64": "inv_level_k10_c3", "fwd_level_kernel<float, 4, 4, 64": "fwd_level_k10_c3",
+           "inv_level_kernel<double, 2, 4, 64": "inv_level_k10_c3", "fwd_level_kernel<double, 2, 4, 64": "fwd_level_k10_c3"}
     # column kernels (col_kernels.cuh): one launch per level and direction
     for t in ("float", "double"):
         for k in (6, 7, 8):
-            fam[f"col_kernel<{t}, {k}, false>"] = f"fwd_level_k{k}_c-3"
-            fam[f"col_kernel<{t}, {k}, true>"] = f"inv_level_k{k}_c-3"
+            fam[f"col_kernel<{t}, {k}, 0>"] = f"fwd_level_k{k}_c-3"
+            fam[f"col_kernel<{t}, {k}, 1>"] = f"inv_level_k{k}_c-3"
     best = {}
     for r in rows[1:]:
         for pat, name in fam.items():
