@@ -27,6 +27,7 @@ def col_deps(k):
 
 
 COL_COMBOS = [(k, f64, inv) for k in (6, 7, 8) for f64 in (0, 1) for inv in (0, 1)]
+COL9_PARTS = 4        # level 9, forward only: gen_col.SPLIT_FWD
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
@@ -36,6 +37,10 @@ def units():
     u = [(os.path.join(OBJ, f"col_{k}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "col_tu.cu"),
           [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}"], col_deps(k))
          for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
+    u = [(os.path.join(OBJ, f"col_9p{p}_{'f64' if f64 else 'f32'}_fwd.o"), os.path.join(CSRC, "col_tu.cu"),
+          ["-DSNFFT_COL_K=9", f"-DSNFFT_COL_PART={p}", f"-DSNFFT_COL_F64={f64}", "-DSNFFT_COL_INV=0"],
+          [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", f"col_gen_9p{p}.cuh")])
+         for f64 in (0, 1) for p in range(COL9_PARTS)] + u
     u.insert(0, (os.path.join(OBJ, "snfft.o"), os.path.join(CSRC, "snfft.cu"), [], MAIN_DEPS))
     u.append((os.path.join(OBJ, "plan.o"), os.path.join(CSRC, "plan.cpp"), [], PLAN_DEPS))
     return u

@@ -1,4 +1,5 @@
-// Column kernels for the level steps k = 6, 7, 8 (generated code col_gen_<k>.cuh, gen_col.py).
+// Column kernels for the level steps k = 6, 7, 8 and the forward step k = 9 (generated code col_gen_<k>.cuh,
+// gen_col.py; level 9 is generated in parts = separate translation units and launches over disjoint child shapes).
 // A thread is (task, column c, instance): it owns the rows of one output column that the bottom sweeps keep
 // together (<= 35 values) in registers, reads its inputs straight from the level array below (lanes over
 // consecutive instances: every global access is a contiguous run) and writes its rows once.  Forward task:
@@ -14,7 +15,7 @@
 #include <stdint.h>
 
 #ifndef SNFFT_COL_K
-#error "col_kernels.cuh: define SNFFT_COL_K (6, 7 or 8) -- one translation unit per level"
+#error "col_kernels.cuh: define SNFFT_COL_K (6..9) -- one translation unit per level (level 9: per part)"
 #endif
 #if SNFFT_COL_K == 6
 #include "col_gen_6.cuh"
@@ -22,9 +23,18 @@
 #include "col_gen_7.cuh"
 #elif SNFFT_COL_K == 8
 #include "col_gen_8.cuh"
+#elif SNFFT_COL_K == 9 && SNFFT_COL_PART == 0
+#include "col_gen_9p0.cuh"
+#elif SNFFT_COL_K == 9 && SNFFT_COL_PART == 1
+#include "col_gen_9p1.cuh"
+#elif SNFFT_COL_K == 9 && SNFFT_COL_PART == 2
+#include "col_gen_9p2.cuh"
+#elif SNFFT_COL_K == 9 && SNFFT_COL_PART == 3
+#include "col_gen_9p3.cuh"
 #endif
 
 namespace snfft {
+namespace {        // internal linkage, see col_gen_<k>.cuh
 
 constexpr int COL_THREADS = 128;
 constexpr int COL_MAXGROUPS = 24;
@@ -82,4 +92,5 @@ __global__ void __launch_bounds__(COL_THREADS, sizeof(T) == 4 ? 5 : 3) col_kerne
     col_run<T, K, INV>(task, c, in + inst, out + inst, (unsigned)ninst);
 }
 
+}  // namespace
 }  // namespace snfft

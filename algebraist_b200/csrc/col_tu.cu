@@ -1,7 +1,7 @@
 // One translation unit per (level, dtype, direction) of the column kernels (col_kernels.cuh): the generated
 // code is large, so the build compiles the eight combinations in parallel.
-//   -DSNFFT_COL_K=7|8  -DSNFFT_COL_F64=0|1  -DSNFFT_COL_INV=0|1
-// Exports  int snfft_col_launch_<K>_<f32|f64>_<fwd|inv>(in, out, ninst, stream)  (0 or a cudaError_t).
+//   -DSNFFT_COL_K=6|7|8|9  -DSNFFT_COL_F64=0|1  -DSNFFT_COL_INV=0|1  [-DSNFFT_COL_PART=0..3 for level 9, forward only]
+// Exports  int snfft_col_launch_<K>[p<part>]_<f32|f64>_<fwd|inv>(in, out, ninst, stream)  (0 or a cudaError_t).
 #ifdef SNFFT_HOST_EMU
 #include "cuda_emu.h"
 #else
@@ -25,10 +25,17 @@ typedef float col_t;
 #else
 #define COL_DIR fwd
 #endif
+#ifdef SNFFT_COL_PART
+#define COL_CAT_(k, part, dt, dir) snfft_col_launch_##k##p##part##_##dt##_##dir
+#define COL_CAT(k, part, dt, dir) COL_CAT_(k, part, dt, dir)
+#define COL_NAME COL_CAT(SNFFT_COL_K, SNFFT_COL_PART, COL_DT, COL_DIR)
+#else
 #define COL_CAT_(k, dt, dir) snfft_col_launch_##k##_##dt##_##dir
 #define COL_CAT(k, dt, dir) COL_CAT_(k, dt, dir)
+#define COL_NAME COL_CAT(SNFFT_COL_K, COL_DT, COL_DIR)
+#endif
 
-extern "C" int COL_CAT(SNFFT_COL_K, COL_DT, COL_DIR)(const void* in, void* out, long long ninst, cudaStream_t st) {
+extern "C" int COL_NAME(const void* in, void* out, long long ninst, cudaStream_t st) {
     using namespace snfft;
     static const int chunk = [] {
         const char* e = std::getenv("SNFFT_COL_CHUNK");       // tuning switch

@@ -31,6 +31,7 @@ from gen_base import Emitter, boffs, children, coef_off, dim, partitions, table
 
 LEVELS = (6, 7, 8)
 CHILD_MAJOR_MAX = 6       # levels whose tasks keep a whole child column in registers
+SPLIT_FWD = {9: 4}        # forward-only levels, generated as several headers / translation units / launches
 
 
 def partner_checked(part, j, t):
@@ -156,16 +157,23 @@ def row_sets(k, part):
     d = dim(part)
     if k <= 7:
         return [list(range(d))]
-    return [list(range(o, o + dim(c))) for c, o in zip(children(part), boffs(part))]
+    if k == 8:
+        return [list(range(o, o + dim(c))) for c, o in zip(children(part), boffs(part))]
+    out = []                    # k = 9: the blocks two levels down (partitions of 7, <= 35 rows)
+    for c, o in zip(children(part), boffs(part)):
+        out += [list(range(o + o2, o + o2 + dim(c2))) for c2, o2 in zip(children(c), boffs(c))]
+    return out
 
 
-def gen_level(k, inverse):
-    """Returns (code, groups, number of tasks, statements)."""
+def gen_level(k, inverse, only=None):
+    """Returns (code, groups, number of tasks, statements); `only`: the child shapes mu (groups) to generate."""
     tag = f"col{k}{'i' if inverse else 'f'}"
     funcs, cases, groups = [], [], []
     total = 0
     task = 0
     for mu in partitions(k - 1):
+        if only is not None and mu not in only:
+            continue
         dm = dim(mu)
         task0 = task
         if not inverse and k <= CHILD_MAJOR_MAX:
@@ -292,33 +300,67 @@ def gen_level(k, inverse):
     return "\n".join(code), groups, task, total
 
 
+def header(k, codes, run_lines):
+    parts = [f"// GENERATED by gen_col.py -- do not edit.  Register column code of the level step k = {k}",
+             "// (see gen_col.py for the derivation and the reference citations).",
+             "#pragma once", "#include <stddef.h>", "",
+             "#ifndef SNFFT_CODE_FENCE",
+             "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")",
+             "#endif", "",
+             "// anonymous namespace: the parts of a split level define the same names with different contents in",
+             "// different translation units (they must not be merged at link time)",
+             "namespace snfft {", "namespace {", "",
+             "template <int K, bool INV> struct ColInfo;", ""] + codes
+    parts.append("template <typename T, int K, bool INV>")
+    parts.append("__device__ __forceinline__ void col_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, unsigned s) {")
+    parts.append(f"    static_assert(K == {k}, \"this translation unit holds the code of one level\");")
+    parts += run_lines
+    parts.append("}")
+    parts.append("")
+    parts.append("}  // namespace")
+    parts.append("}  // namespace snfft")
+    return "\n".join(parts) + "\n"
+
+
+def write_if_changed(path, text):
+    if not os.path.exists(path) or open(path).read() != text:      # untouched levels keep their objects
+        with open(path, "w") as fh:
+            fh.write(text)
+
+
+def split_groups(k, inverse, nparts):
+    """Child shapes of level k in `nparts` sets of about equal generated code (largest first, greedy)."""
+    cost = {mu: gen_level(k, inverse, only={mu})[3] for mu in partitions(k - 1)}
+    sets, load = [set() for _ in range(nparts)], [0] * nparts
+    for mu in sorted(cost, key=lambda m: -cost[m]):
+        p = load.index(min(load))
+        sets[p].add(mu)
+        load[p] += cost[mu]
+    return sets
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
     stats = {}
     for k in LEVELS:            # one header per level: a translation unit only sees (and depends on) its own
-        parts = [f"// GENERATED by gen_col.py -- do not edit.  Register column code of the level step k = {k}",
-                 "// (see gen_col.py for the derivation and the reference citations).",
-                 "#pragma once", "#include <stddef.h>", "",
-                 "#ifndef SNFFT_CODE_FENCE",
-                 "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")",
-                 "#endif", "", "namespace snfft {", "",
-                 "template <int K, bool INV> struct ColInfo;", ""]
+        codes = []
         for inverse in (False, True):
             code, groups, ntask, n = gen_level(k, inverse)
             stats[(k, inverse)] = (ntask, n)
-            parts.append(code)
-        parts.append("template <typename T, int K, bool INV>")
-        parts.append("__device__ __forceinline__ void col_run(int task, int c, const T* __restrict__ in, T* __restrict__ out, unsigned s) {")
-        parts.append(f"    static_assert(K == {k}, \"this translation unit holds the code of one level\");")
-        parts.append(f"    if constexpr (!INV) col{k}f_run<T>(task, c, in, out, s);")
-        parts.append(f"    else col{k}i_run<T>(task, c, in, out, s);")
-        parts.append("}")
-        parts.append("")
-        parts.append("}  // namespace snfft")
-        path, text = os.path.join(here, f"col_gen_{k}.cuh"), "\n".join(parts) + "\n"
-        if not os.path.exists(path) or open(path).read() != text:      # untouched levels keep their objects
-            with open(path, "w") as fh:
-                fh.write(text)
+            codes.append(code)
+        write_if_changed(os.path.join(here, f"col_gen_{k}.cuh"),
+                         header(k, codes, [f"    if constexpr (!INV) col{k}f_run<T>(task, c, in, out, s);",
+                                           f"    else col{k}i_run<T>(task, c, in, out, s);"]))
+    for k, nparts in SPLIT_FWD.items():      # forward only, one header (= one kernel launch) per set of child shapes
+        tot = [0, 0]
+        for p, only in enumerate(split_groups(k, False, nparts)):
+            code, groups, ntask, n = gen_level(k, False, only=only)
+            tot[0] += ntask
+            tot[1] += n
+            write_if_changed(os.path.join(here, f"col_gen_{k}p{p}.cuh"),
+                             header(k, [code], ["    static_assert(!INV, \"forward only\");",
+                                                f"    col{k}f_run<T>(task, c, in, out, s);"]))
+        stats[(k, False)] = tuple(tot)
     print("(level, inverse): (tasks, statements)", stats)
 
 

@@ -623,8 +623,13 @@ extern "C" {
 SNFFT_COL_DECL(6, f32) SNFFT_COL_DECL(6, f64) SNFFT_COL_DECL(7, f32) SNFFT_COL_DECL(7, f64) SNFFT_COL_DECL(8, f32)
 SNFFT_COL_DECL(8, f64)
 #undef SNFFT_COL_DECL
+#define SNFFT_COL9_DECL(p) \
+    int snfft_col_launch_9p##p##_f32_fwd(const void*, void*, long long, cudaStream_t); \
+    int snfft_col_launch_9p##p##_f64_fwd(const void*, void*, long long, cudaStream_t);
+SNFFT_COL9_DECL(0) SNFFT_COL9_DECL(1) SNFFT_COL9_DECL(2) SNFFT_COL9_DECL(3)
+#undef SNFFT_COL9_DECL
 }
-constexpr int kColFirst = 6, kColLast = 8;
+constexpr int kColFirst = 6, kColLast = 9, kColLastInv = 8;      // level 9: forward only, four launches
 
 // Levels that use the column kernels: automatic kernel choice only (the forced TB / sweep modes of
 // snfft_debug_tb_mode keep testing those families), SNFFT_COL_FWD / SNFFT_COL_INV (lists of levels) override.
@@ -632,7 +637,7 @@ static void col_pick_dirs(int k, bool* fwd, bool* inv) {
     *fwd = *inv = false;
     if (k < kColFirst || k > kColLast || g_tb_mode.load() != -1) return;
     *fwd = tb_level_listed("SNFFT_COL_FWD", k, true);
-    *inv = tb_level_listed("SNFFT_COL_INV", k, true);
+    *inv = k <= kColLastInv && tb_level_listed("SNFFT_COL_INV", k, true);
 }
 
 template <typename T, bool INVERSE>
@@ -640,6 +645,20 @@ static int run_col_level(const snfft_plan* p, int k, const void* in, void* out, 
     const long long ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
     ProfScope prof(p, st, INVERSE ? 1 : 0, k, -3, p->host.factorial[k]);
     int rc;
+    if (k == 9) {                       // forward only: one launch per set of child shapes
+        if (INVERSE) return set_error(SNFFT_ENOTSUP, "no inverse column kernel at level 9");
+        typedef int (*fn_t)(const void*, void*, long long, cudaStream_t);
+        static const fn_t f32[4] = {snfft_col_launch_9p0_f32_fwd, snfft_col_launch_9p1_f32_fwd, snfft_col_launch_9p2_f32_fwd,
+                                    snfft_col_launch_9p3_f32_fwd};
+        static const fn_t f64[4] = {snfft_col_launch_9p0_f64_fwd, snfft_col_launch_9p1_f64_fwd, snfft_col_launch_9p2_f64_fwd,
+                                    snfft_col_launch_9p3_f64_fwd};
+        for (int part = 0; part < 4; ++part) {
+            rc = (sizeof(T) == 4 ? f32 : f64)[part](in, out, ninst, st);
+            g_launches.fetch_add(1);
+            if (rc) return set_error(SNFFT_ECUDA, std::string("column kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+        }
+        return SNFFT_OK;
+    }
 #define SNFFT_COL_CALL(kk, dt) (INVERSE ? snfft_col_launch_##kk##_##dt##_inv(in, out, ninst, st) : snfft_col_launch_##kk##_##dt##_fwd(in, out, ninst, st))
     if (sizeof(T) == 4) rc = k == 6 ? SNFFT_COL_CALL(6, f32) : (k == 7 ? SNFFT_COL_CALL(7, f32) : SNFFT_COL_CALL(8, f32));
     else rc = k == 6 ? SNFFT_COL_CALL(6, f64) : (k == 7 ? SNFFT_COL_CALL(7, f64) : SNFFT_COL_CALL(8, f64));
