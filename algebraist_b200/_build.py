@@ -46,6 +46,20 @@ def units():
     return u
 
 
+def generate_col_headers(force: bool = False):
+    """col_gen_<k>.cuh (20 MB of straight-line code) are not kept in git: csrc/gen_col.py writes them (2 s)."""
+    gens = [os.path.join(CSRC, f) for f in ("gen_col.py", "gen_base.py")]
+    heads = [os.path.join(CSRC, f"col_gen_{k}.cuh") for k in (6, 7, 8)] + [
+        os.path.join(CSRC, f"col_gen_9p{p}.cuh") for p in range(COL9_PARTS)]
+    if force or any(stale(h, gens) for h in heads):
+        res = subprocess.run([sys.executable, os.path.join(CSRC, "gen_col.py")], capture_output=True, text=True, cwd=CSRC)
+        if res.returncode != 0:
+            raise RuntimeError("gen_col.py failed:\n" + res.stdout + res.stderr)
+        for h in heads:             # unchanged headers keep their contents and objects; mark them as checked
+            if os.path.getmtime(h) < max(os.path.getmtime(g) for g in gens):
+                os.utime(h)
+
+
 def stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -54,6 +68,7 @@ def stale(target, deps):
 
 
 def needs_build() -> bool:
+    generate_col_headers()
     return any(stale(o, d) for o, _, _, d in units()) or stale(OUT, [o for o, _, _, _ in units()])
 
 
@@ -64,6 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: the sm_100a library cannot be built")
     os.makedirs(OBJ, exist_ok=True)
+    generate_col_headers()
     todo = [u for u in units() if force or stale(u[0], u[3])]
 
     def compile_one(u):

@@ -184,6 +184,8 @@ int snfft_dense_rep(snfft_plan_t* plan, int part, void* out, void* stream);
  *   kind: 0 forward level, 1 inverse level, 2 input gather, 3 output scatter,
  *         4 forward base kernels (level = 5: levels 2..5 in registers; level = 6: level 6),
  *         5 inverse base kernels (same levels), 6 pack (top level -> [lambda][B][d][d]), 7 unpack
+ *   kernel_class: 0..5 sweep-per-pass classes, >= 10 the fused-top / register-bottom (TB) kernels, -1 generated base kernels, -2 data
+ *         movement, -3 the register column kernels (levels 6..8, forward level 9: col_kernels.cuh)
  *   elems_per_instance: coefficients the launch produces per function
  *     (its share of k!; the launch reads as many), so its algorithmic traffic
  *     is 2 * elems_per_instance * NINST_level * sizeof(dtype) bytes.

@@ -42,6 +42,7 @@ def build_emu():
     from algebraist_b200 import _build as PB
     bdir = os.path.dirname(EMU_SO)
     os.makedirs(bdir, exist_ok=True)
+    PB.generate_col_headers()
     emu_h = os.path.join(EMU_DIR, "cuda_emu.h")
     units = [(os.path.join(bdir, os.path.basename(obj)), src, extra, deps + [emu_h]) for obj, src, extra, deps in PB.units()]
     todo = [u for u in units if PB.stale(u[0], u[3])]
