@@ -9,6 +9,7 @@
 #define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "col_kernels.cuh"
@@ -38,8 +39,15 @@ typedef float col_t;
 extern "C" int COL_NAME(const void* in, void* out, long long ninst, cudaStream_t st) {
     using namespace snfft;
     static const int chunk = [] {
-        const char* e = std::getenv("SNFFT_COL_CHUNK");       // tuning switch
-        return e ? std::atoi(e) : 148;
+        // tiles of one task that run before the next task of the group (col_kernels.cuh); tuning switches:
+        // SNFFT_COL_CHUNK_<K> for one level, SNFFT_COL_CHUNK for all
+        char name[32];
+        std::snprintf(name, sizeof name, "SNFFT_COL_CHUNK_%d", SNFFT_COL_K);
+        const char* e = std::getenv(name);
+        if (!e) e = std::getenv("SNFFT_COL_CHUNK");
+        if (e) return std::atoi(e);
+        // measured (profiles r01l): level 9 forward 74, level 8 100, level 7 inverse 74, otherwise one wave of 148
+        return SNFFT_COL_K == 9 ? 74 : (SNFFT_COL_K == 8 ? 100 : (SNFFT_COL_K == 7 && SNFFT_COL_INV ? 74 : 148));
     }();
     const ColGroups g = col_groups<SNFFT_COL_K, SNFFT_COL_INV != 0>(ninst, chunk);
     const unsigned nblk = g.blk0[g.ngroups];

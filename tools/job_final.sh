@@ -11,3 +11,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 ncu --set full --clock-control none --kernel-name-base demangled -k 'regex:level_kernel|tb_kernel|col_kernel' -f -o /tmp/prof_final python tools/prof_step.py --n 10 --batch 128 > gpurun_out/ncu_final.log 2>&1; echo "full rc=$?"
 python tools/ncu_summary.py /tmp/prof_final.ncu-rep gpurun_out/ncu_levels_$TAG.csv > /dev/null
 python tools/ncu_traffic.py gpurun_out/ncu_levels_$TAG.csv 128 f32 gpurun_out/traffic_$TAG.json
+python bench.py --workload coset --steps 5 --warmup 3 > gpurun_out/bench_${TAG}_coset_n1.json 2> gpurun_out/bench_${TAG}_coset_n1.err; echo "coset rc=$?"
