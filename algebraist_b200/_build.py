@@ -28,17 +28,23 @@ def col_deps(k):
 
 COL_COMBOS = [(k, f64, inv) for k in (6, 7, 8) for f64 in (0, 1) for inv in (0, 1)]
 COL9_PARTS = 4        # level 9, forward only: gen_col.SPLIT_FWD
+# threads per CTA of the column kernels by (level, fp64); default 128.  One large CTA per SM keeps all its warps on
+# the code of ONE task (instruction fetch was the top stall at levels 8 and 9 with five 128-thread CTAs of
+# different tasks per SM): forward k = 9 3.36 -> 2.30 ms, fp64 5.6 -> 3.7 ms; level 7 is faster with 128.
+COL_THREADS = {(9, 0): 640, (8, 0): 640, (9, 1): 384, (8, 1): 384}
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
 def units():
     """(object, source, extra flags, dependencies); the largest translation units first."""
-    u = [(os.path.join(OBJ, f"col_{k}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "col_tu.cu"),
-          [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}"], col_deps(k))
+    u = [(os.path.join(OBJ, f"col_{k}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}_t{COL_THREADS.get((k, f64), 128)}.o"), os.path.join(CSRC, "col_tu.cu"),
+          [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}",
+           f"-DSNFFT_COL_THREADS={COL_THREADS.get((k, f64), 128)}"], col_deps(k))
          for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
-    u = [(os.path.join(OBJ, f"col_9p{p}_{'f64' if f64 else 'f32'}_fwd.o"), os.path.join(CSRC, "col_tu.cu"),
-          ["-DSNFFT_COL_K=9", f"-DSNFFT_COL_PART={p}", f"-DSNFFT_COL_F64={f64}", "-DSNFFT_COL_INV=0"],
+    u = [(os.path.join(OBJ, f"col_9p{p}_{'f64' if f64 else 'f32'}_fwd_t{COL_THREADS.get((9, f64), 128)}.o"), os.path.join(CSRC, "col_tu.cu"),
+          ["-DSNFFT_COL_K=9", f"-DSNFFT_COL_PART={p}", f"-DSNFFT_COL_F64={f64}", "-DSNFFT_COL_INV=0",
+           f"-DSNFFT_COL_THREADS={COL_THREADS.get((9, f64), 128)}"],
           [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", f"col_gen_9p{p}.cuh")])
          for f64 in (0, 1) for p in range(COL9_PARTS)] + u
     u.insert(0, (os.path.join(OBJ, "snfft.o"), os.path.join(CSRC, "snfft.cu"), [], MAIN_DEPS))

@@ -36,7 +36,10 @@
 namespace snfft {
 namespace {        // internal linkage, see col_gen_<k>.cuh
 
-constexpr int COL_THREADS = 128;
+#ifndef SNFFT_COL_THREADS
+#define SNFFT_COL_THREADS 128
+#endif
+constexpr int COL_THREADS = SNFFT_COL_THREADS;     // per level (build flag): large CTAs keep the warps of an SM on one task's code
 constexpr int COL_MAXGROUPS = 24;
 
 struct ColGroups {
@@ -68,7 +71,7 @@ inline ColGroups col_groups(long long ninst, int chunk) {
 // Register cap: ptxas hoists the (read-only) loads of a whole task as far as the register file allows, which without
 // a cap means 255 registers and spills; MINB CTAs per SM bound it (fp32: 102 registers, fp64: 170).
 template <typename T, int K, bool INV>
-__global__ void __launch_bounds__(COL_THREADS, sizeof(T) == 4 ? 5 : 3) col_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst,
+__global__ void __launch_bounds__(COL_THREADS, (sizeof(T) == 4 ? 640 : 384) / COL_THREADS) col_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst,
                                                           const ColGroups g) {
     const unsigned b = blockIdx.x;
     int gi = 0;

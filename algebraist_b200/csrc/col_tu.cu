@@ -46,8 +46,9 @@ extern "C" int COL_NAME(const void* in, void* out, long long ninst, cudaStream_t
         const char* e = std::getenv(name);
         if (!e) e = std::getenv("SNFFT_COL_CHUNK");
         if (e) return std::atoi(e);
-        // measured (profiles r01l): level 9 forward 74, level 8 100, level 7 inverse 74, otherwise one wave of 148
-        return SNFFT_COL_K == 9 ? 74 : (SNFFT_COL_K == 8 ? 100 : (SNFFT_COL_K == 7 && SNFFT_COL_INV ? 74 : 148));
+        // measured (profiles r01l/r01m), with the CTA sizes of _build.py (640 / 384 threads at levels 8 and 9, 128 below):
+        // level 9 forward 4 tiles, level 8 16 (fp64: 8), level 7 inverse 74, otherwise one wave of 148
+        return SNFFT_COL_K == 9 ? 4 : (SNFFT_COL_K == 8 ? (SNFFT_COL_F64 ? 8 : 16) : (SNFFT_COL_K == 7 && SNFFT_COL_INV ? 74 : 148));
     }();
     const ColGroups g = col_groups<SNFFT_COL_K, SNFFT_COL_INV != 0>(ninst, chunk);
     const unsigned nblk = g.blk0[g.ngroups];

@@ -60,6 +60,64 @@ def _inverse_packed(plan, packed: torch.Tensor, batch: int) -> torch.Tensor:
     return out
 
 
+def _scale_blocks(plan, packed: torch.Tensor, batch: int, inverse_weights: bool) -> torch.Tensor:
+    """packed * diag(w_lambda), w = n!/d_lambda (inverse_weights) or d_lambda/n!, in place."""
+    views = [packed[off * batch:(off + d * d) * batch] for d, off in zip(plan.dims, plan.offsets)]
+    w = [plan.nfact / d if inverse_weights else d / plan.nfact for d in plan.dims]
+    torch._foreach_mul_(views, w)
+    return packed
+
+
+class _ForwardFn(torch.autograd.Function):
+    """Autograd for sn_fft.  The reference transform is a composition of differentiable torch ops
+    (einsum / matmul, fourier.py:111-131, 223-278), so callers may backpropagate through it.  The transform
+    T is linear and T^-1 = T^T diag(d_lambda / n!) (Plancherel), hence T^T g = T^-1 (n!/d_lambda g): the
+    backward pass is the inverse pipeline on rescaled gradients."""
+
+    @staticmethod
+    def forward(ctx, f2d, n):
+        plan, packed = _forward_packed(f2d, n)
+        ctx.plan, ctx.batch = plan, f2d.shape[0]
+        batch = ctx.batch
+        outs = tuple(packed[off * batch:(off + d * d) * batch] for d, off in zip(plan.dims, plan.offsets))
+        return outs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        plan, batch = ctx.plan, ctx.batch
+        like = next(g for g in grads if g is not None)
+        packed = torch.zeros(batch * plan.nfact, dtype=like.dtype, device=like.device)
+        for g, d, off in zip(grads, plan.dims, plan.offsets):
+            if g is not None:
+                packed[off * batch:(off + d * d) * batch].copy_(g.reshape(-1))
+        _scale_blocks(plan, packed, batch, inverse_weights=True)
+        return _inverse_packed(plan, packed, batch), None
+
+
+class _InverseFn(torch.autograd.Function):
+    """Autograd for sn_ifft: (T^-1)^T h = diag(d_lambda / n!) T h, the forward pipeline on the incoming
+    gradient with every block rescaled."""
+
+    @staticmethod
+    def forward(ctx, n, batch, *pieces):
+        some = pieces[0]
+        plan = get_plan(n, some.dtype, some.device)
+        packed = torch.cat([p.reshape(-1) for p in pieces])
+        ctx.plan, ctx.batch, ctx.shapes, ctx.n = plan, batch, [tuple(p.shape) for p in pieces], n
+        return _inverse_packed(plan, packed, batch)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        plan, batch = ctx.plan, ctx.batch
+        _, packed = _forward_packed(grad_out.reshape(batch, plan.nfact).contiguous(), ctx.n)
+        _scale_blocks(plan, packed, batch, inverse_weights=False)
+        grads = tuple(packed[off * batch:(off + d * d) * batch].view(shape)
+                      for d, off, shape in zip(plan.dims, plan.offsets, ctx.shapes))
+        return (None, None) + grads
+
+
 def _check_input(fn_vals, n):
     if not isinstance(fn_vals, torch.Tensor):
         raise TypeError("fn_vals must be a torch.Tensor")
@@ -83,11 +141,15 @@ def sn_fft(fn_vals: torch.Tensor, n: int, verbose: bool = False) -> dict:
     x, home = _to_device(fn_vals)
     lead = tuple(x.shape[:-1])
     f2d = x.reshape(-1, x.shape[-1]).contiguous()
-    plan, packed = _forward_packed(f2d, n)
     batch = f2d.shape[0]
+    if torch.is_grad_enabled() and f2d.requires_grad and batch:
+        plan = get_plan(n, f2d.dtype, f2d.device)
+        blocks = _ForwardFn.apply(f2d, n)
+    else:
+        plan, packed = _forward_packed(f2d, n)
+        blocks = [packed[off * batch:(off + d * d) * batch] for d, off in zip(plan.dims, plan.offsets)]
     result = {}
-    for lam, d, off in zip(plan.partitions, plan.dims, plan.offsets):
-        blk = packed[off * batch:(off + d * d) * batch]
+    for lam, d, blk in zip(plan.partitions, plan.dims, blocks):
         if d == 1:
             val = blk.view(lead)
         else:
@@ -143,8 +205,21 @@ def sn_ifft(ft: dict, n: int) -> torch.Tensor:
     this returns the mathematical inverse
         f(sigma) = 1/n! sum_lambda d_lambda <F(lambda), rho_lambda(sigma)>
     at every n, shape leading + (n!,) (squeezed for n <= 5 like the reference)."""
-    plan, packed, batch, lead, home = _pack_ft(ft, n)
-    out = _inverse_packed(plan, packed, batch).view(lead + (plan.nfact,))
+    if torch.is_grad_enabled() and any(isinstance(v, torch.Tensor) and v.requires_grad for v in ft.values()):
+        some = next(iter(ft.values()))
+        x, home = _to_device(some)
+        plan = get_plan(n, x.dtype, x.device)
+        lead = tuple(ft[plan.partitions[0]].shape)
+        batch = ft[plan.partitions[0]].numel()
+        pieces = []
+        for lam, d in zip(plan.partitions, plan.dims):
+            if lam not in ft or ft[lam].numel() != batch * d * d:
+                raise ValueError(f"ft[{lam}] is missing or has the wrong number of elements")
+            pieces.append(ft[lam].to(device=x.device, dtype=x.dtype))
+        out = _InverseFn.apply(n, batch, *pieces).view(lead + (plan.nfact,))
+    else:
+        plan, packed, batch, lead, home = _pack_ft(ft, n)
+        out = _inverse_packed(plan, packed, batch).view(lead + (plan.nfact,))
     if n <= BASE_CASE:
         out = out.squeeze()
     return out if home == out.device else out.to(home)

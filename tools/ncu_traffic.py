@@ -34,7 +34,7 @@ def main():
     best = {}
     for r in rows[1:]:
         for pat, name in fam.items():
-            if r[ki].startswith(pat):
+            if r[ki].startswith(pat) or ("col_kernel" in pat and pat in r[ki]):
                 t = float(r[ti].split()[0])
                 if name not in best or t > best[name][0]:
                     best[name] = (t, to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
