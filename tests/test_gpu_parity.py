@@ -309,3 +309,55 @@ def test_stream_batches_host_pipeline(A):
     ft_host = A.stream_batches(lambda x: A.sn_fft(x, n)[(n - 1, 1)], f_host, chunk=16)
     ref = A.sn_fft(f_host.cuda(), n)[(n - 1, 1)].cpu()
     assert torch.equal(ft_host, ref)
+
+
+@pytest.mark.parametrize("n,B", [(8, 1), (8, 33), (9, 1), (9, 5), (9, 37), (10, 3)])
+def test_ragged_batches_full_pipeline(A, n, B):
+    """Batches that are not a multiple of 4 / 128 (scalar transfers, ragged last tiles of the column kernels):
+    row 0 against the oracle, every row against the transform of that row alone, round trip."""
+    rng = np.random.default_rng(1000 * n + B)
+    f = rng.standard_normal((B, math.factorial(n)))
+    x = torch.from_numpy(f).float().cuda()
+    ft = A.sn_fft(x, n)
+    _check_dict({lam: v[:1] for lam, v in ft.items()}, O.sn_fft_packed(f[:1], n), 1e-5)
+    last = A.sn_fft(x[B - 1:], n)
+    for lam, v in ft.items():
+        assert (v[B - 1:] - last[lam]).double().norm().item() <= 1e-6 * max(last[lam].double().norm().item(), 1e-30)
+    assert rel_err(A.sn_ifft(ft, n).cpu().numpy(), f) < 1e-5
+
+
+def test_config2_s8_batch_4096(A):
+    """BASELINE config 2: forward FFT on S_8, batch 4096 fp32 (661 MB).  Rows 0..3 against the reference's golden
+    outputs (same inputs), Plancherel and round trip on every row."""
+    n, B = 8, 4096
+    g = load_transform_golden(n)
+    f4 = torch.from_numpy(g[f"n{n}_f32_f"])
+    nf = math.factorial(n)
+    torch.manual_seed(8)
+    f = torch.randn(B, nf, device="cuda")
+    f[:f4.shape[0]] = f4.cuda()
+    ft = A.sn_fft(f, n)
+    for lam, v in ft.items():
+        ref = g[f"n{n}_f32_ft_{key(lam)}"]
+        assert rel_err(v[:f4.shape[0]].cpu().numpy().reshape(ref.shape), ref) < 1e-5, lam
+    power = sum(v.double().reshape(B, -1).pow(2).sum(1) * (1 if v.dim() == 1 else v.shape[-1]) / nf for v in ft.values())
+    ref = f.double().pow(2).sum(1)
+    assert ((power - ref).abs() / ref).max().item() < 1e-4
+    inv = A.sn_ifft(ft, n)
+    assert ((inv - f).double().norm(dim=1) / f.double().norm(dim=1)).max().item() < 1e-5
+
+
+def test_n12_single_function_round_trip(A):
+    """One function on S_12 (479 M values, 1.9 GB): the largest n of the C ABI; levels 6..9 run the column kernels
+    with NINST = 12!/k! instances.  Round trip and Plancherel."""
+    n = 12
+    nf = math.factorial(n)
+    torch.manual_seed(12)
+    f = torch.randn(1, nf, device="cuda")
+    ft = A.sn_fft(f, n)
+    power = sum(v.double().reshape(1, -1).pow(2).sum(1) * (1 if v.dim() == 1 else v.shape[-1]) / nf for v in ft.values())
+    ref = f.double().pow(2).sum(1)
+    assert ((power - ref).abs() / ref).max().item() < 1e-4
+    inv = A.sn_ifft(ft, n)
+    del ft
+    assert ((inv - f).double().norm() / f.double().norm()).item() < 1e-5
