@@ -60,7 +60,7 @@ def chunk_schedule(batch: int, chunk: int, ramp: bool = True):
 
 
 def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, chunk: int = 32, device=None,
-                   ramp: bool = True):
+                   ramp: bool = True, nslots: int = 3):
     """Apply `fn` to the rows of `src_host` chunk by chunk on `device`, writing the results to `dst_host`.
 
     src_host : (B, ...) host tensor; pin it (`.pin_memory()`) or the copies cannot overlap anything.
@@ -77,7 +77,7 @@ def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, ch
         return dst_host if dst_host is not None else src_host.new_empty(src_host.shape)
     compute = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    nslots = 2                                         # double buffering of the device-side input / output chunks
+    nslots = max(2, int(nslots))                       # device-side input / output chunk buffers in flight
     ins = [None] * nslots
     outs = [None] * nslots
     in_ready = [None] * nslots                         # copy-in of the chunk in slot s finished
@@ -106,12 +106,13 @@ def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, ch
             in_ready[s] = torch.cuda.Event()
             in_ready[s].record(s_in)
 
-    copy_in(0)
+    for c in range(min(nslots - 1, nchunks)):
+        copy_in(c)
     for c in range(nchunks):
         s = c % nslots
         lo, hi = bounds[c], bounds[c + 1]
-        if c + 1 < nchunks:
-            copy_in(c + 1)                             # overlaps the transform of chunk c
+        if c + nslots - 1 < nchunks:
+            copy_in(c + nslots - 1)                    # nslots - 1 chunks ahead: overlaps the transforms before it
         compute.wait_event(in_ready[s])
         if out_free[s] is not None:
             compute.wait_event(out_free[s])            # the previous result in this slot has left the device

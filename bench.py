@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the process to the GPU's NUMA node for the e2e leg")
+    ap.add_argument("--e2e-slots", type=int, default=3, help="chunk buffers in flight in the end-to-end pipeline")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="functions per chunk of the end-to-end pipeline (0 = batch / 8)")
     ap.add_argument("--workload", default="batch", choices=["batch", "coset"],
                     help="batch: BASELINE configs 2-4 (default); coset: config 5, ONE S_n function (default n = 11) sharded "
@@ -271,7 +272,8 @@ def run_native(a):
     def e2e_step():
         # public API for host-resident batches: chunks of the batch stream through the GPU, the copies of
         # chunk i+1 / i-1 overlap the transform of chunk i (all of them are inside the timed region)
-        stream_batches(lambda x: sn_ifft(sn_fft(x, n), n), f_host, out_host, chunk=e2e_chunk, device=dev)
+        stream_batches(lambda x: sn_ifft(sn_fft(x, n), n), f_host, out_host, chunk=e2e_chunk, device=dev,
+                       nslots=a.e2e_slots)
 
     for _ in range(3):
         e2e_step()

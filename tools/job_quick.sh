@@ -1,2 +1,4 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ragged or config2 or n12" > gpurun_out/pytest_edge.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_edge.log
-python bench.py --steps 5 --warmup 3 --n 8 --batch 4096 --no-cpu-baseline > gpurun_out/bench_s8_b4096.json 2> gpurun_out/bench_s8_b4096.err; echo "bench s8 rc=$?"
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r01n.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_r01n.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r01n.log 2>&1; echo "smoke rc=$?"
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01n.json 2> gpurun_out/bench_r01n.err; echo "bench rc=$?"
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-chunk 24 > gpurun_out/bench_r01n_c24.json 2> gpurun_out/bench_r01n_c24.err; echo "bench rc=$?"
