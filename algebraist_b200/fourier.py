@@ -262,6 +262,33 @@ def calc_power(ft: dict, n: int) -> dict:
     return result
 
 
+def sn_convolve(f: torch.Tensor, g: torch.Tensor, n: int) -> torch.Tensor:
+    """Group convolution through the transform (the reference tests the theorem at
+    tests/test_fourier.py:87-109 with the direct sum of tests/test_fourier.py:22-34):
+
+        (f * g)(pi) = sum_sigma f(sigma) g(pi sigma^-1)        <=>        FT(f * g) = FT(g) @ FT(f)
+
+    f, g: (n!,) or (..., n!) with equal shapes; returns the same shape.  Both transforms and the inverse run in
+    this package's kernels; the per-partition d x d products are batched `torch.matmul` calls (cuBLAS: a library
+    GEMM, not one of this package's kernels)."""
+    _check_input(f, n)
+    _check_input(g, n)
+    if f.shape != g.shape or f.dtype != g.dtype:
+        raise ValueError("f and g must have the same shape and dtype")
+    xf, home = _to_device(f)
+    xg, _ = _to_device(g)
+    xg = xg.to(xf.device)
+    plan, pf = _forward_packed(xf.reshape(-1, xf.shape[-1]).contiguous(), n)
+    _, pg = _forward_packed(xg.reshape(-1, xg.shape[-1]).contiguous(), n)
+    batch = pf.numel() // plan.nfact
+    prod = torch.empty_like(pf)
+    for d, off in zip(plan.dims, plan.offsets):
+        blk = slice(off * batch, (off + d * d) * batch)
+        torch.matmul(pg[blk].view(batch, d, d), pf[blk].view(batch, d, d), out=prod[blk].view(batch, d, d))
+    out = _inverse_packed(plan, prod, batch).view(tuple(f.shape))
+    return out if home == out.device else out.to(home)
+
+
 def _dense_rep(plan, part: int) -> torch.Tensor:
     d = plan.dims[part]
     out = torch.empty((plan.nfact, d, d), dtype=plan.dtype, device=plan.device)

@@ -113,3 +113,27 @@ def next_rows():
         for lam, v in RF.calc_power(one, n).items():
             out[f"n{n}_power1_{key(lam)}"] = np.asarray(v.numpy())
     np.savez_compressed(os.path.join(OUT, "next_rows.npz"), **out)
+
+
+def convolution():
+    """tests/golden/convolution.npz: group convolution exactly as the reference's own test helper computes it
+    (tests/test_fourier.py:22-34: result[i] = sum_j f[j] * g[index(perms[i] * perms[j].inverse)], with the
+    reference's `Permutation` product and `full_group` order), n = 3..5, fp64, seeded inputs.  The convolution
+    theorem the reference tests (tests/test_fourier.py:87-109) is FT(convolve(g, f)) = FT(f) @ FT(g).
+
+        python -c "import sys; sys.path.insert(0, 'oracle'); import make_golden as M; M.convolution()"
+    """
+    from algebraist.permutations import Permutation
+    out = {}
+    for n in range(3, 6):
+        perms = list(Permutation.full_group(n))
+        index = {p.sigma: i for i, p in enumerate(perms)}
+        torch.manual_seed(2000 + n)
+        f = torch.randn(math.factorial(n), dtype=torch.float64).numpy()
+        g = torch.randn(math.factorial(n), dtype=torch.float64).numpy()
+        res = np.zeros_like(f)
+        for i, pi in enumerate(perms):
+            for j, sigma in enumerate(perms):
+                res[i] += f[j] * g[index[(pi * sigma.inverse).sigma]]
+        out[f"n{n}_f"], out[f"n{n}_g"], out[f"n{n}_conv_f_g"] = f, g, res        # = convolve(f, g, n) of the test helper
+    np.savez_compressed(os.path.join(OUT, "convolution.npz"), **out)
