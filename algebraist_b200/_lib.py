@@ -47,6 +47,7 @@ SIGNATURES = {
     "snfft_forward_cosets": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_int), c_int, c_vp, c_vp, ctypes.c_size_t,
                                      c_vp]),
     "snfft_power": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "snfft_block_matmul": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "snfft_forward_host": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "snfft_inverse_host": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "snfft_perm_rank": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp]),

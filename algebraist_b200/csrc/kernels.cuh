@@ -1132,4 +1132,66 @@ __global__ void __launch_bounds__(32) dense_rep_kernel(const RowTables<T> tb, in
     for (int t = 0; t < d; ++t) out[(rank * d + t) * d + c] = x[t * 32 + lane];
 }
 
+
+// ---------------------------------------------------------------------------
+// Per-partition products of two packed coefficient arrays: C_lambda[b] = A_lambda[b] . B_lambda[b]
+// (d x d, row major), the Fourier side of the convolution theorem (reference tests/test_fourier.py:87-109).
+// One launch per partition; a CTA owns a 64 x 64 tile of one batch row, 256 threads x (4 x 4) outputs,
+// K in steps of 16 through shared memory (A stored transposed so both operand reads are conflict free).
+// Plain FFMA / DFMA: the parity contract is fp32 1e-5 / fp64 1e-12, which rules out the TF32 tensor path.
+// ---------------------------------------------------------------------------
+constexpr int MM_TILE = 64, MM_K = 16, MM_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(MM_THREADS) block_matmul_kernel(const T* __restrict__ A, const T* __restrict__ B,
+                                                                  T* __restrict__ C, int d, int tiles) {
+    __shared__ T As[MM_K][MM_TILE + 4];
+    __shared__ T Bs[MM_K][MM_TILE + 4];
+    const int tid = threadIdx.x;
+    const long long blk = blockIdx.x;
+    const long long b = blk / ((long long)tiles * tiles);
+    const int rem = (int)(blk - b * (long long)tiles * tiles);
+    const int m0 = (rem / tiles) * MM_TILE, n0 = (rem % tiles) * MM_TILE;
+    const T* __restrict__ a = A + (size_t)b * d * d;
+    const T* __restrict__ bm = B + (size_t)b * d * d;
+    const int ty = tid / 16, tx = tid % 16;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int k0 = 0; k0 < d; k0 += MM_K) {
+        // A tile: 64 rows x 16 k, thread -> (row = e / 16, k = e % 16); B tile: 16 k x 64 columns
+#pragma unroll
+        for (int e = tid; e < MM_TILE * MM_K; e += MM_THREADS) {
+            const int r = e / MM_K, kk = e % MM_K;
+            As[kk][r] = (m0 + r < d && k0 + kk < d) ? a[(size_t)(m0 + r) * d + k0 + kk] : T(0);
+            const int kb = e / MM_TILE, cc = e % MM_TILE;
+            Bs[kb][cc] = (k0 + kb < d && n0 + cc < d) ? bm[(size_t)(k0 + kb) * d + n0 + cc] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < MM_K; ++kk) {
+            T av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+        }
+        __syncthreads();
+    }
+    T* __restrict__ c = C + (size_t)b * d * d;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = m0 + ty * 4 + i, cc = n0 + tx * 4 + j;
+            if (r < d && cc < d) c[(size_t)r * d + cc] = acc[i][j];
+        }
+}
+
 }  // namespace snfft

@@ -1052,6 +1052,33 @@ int snfft_forward_cosets(const snfft_plan_t* pn, const snfft_plan_t* pm, const v
                                   : forward_cosets_impl<double>(pn, pm, f, B, cosets, ncosets, F, ws, st);
 }
 
+int snfft_block_matmul(const snfft_plan_t* p, const void* A, const void* Bm, void* C, int64_t B, void* stream) {
+    if (!p) return set_error(SNFFT_EINVAL, "plan is NULL");
+    if (B < 0) return set_error(SNFFT_EINVAL, "negative batch");
+    if (B == 0) return SNFFT_OK;
+    if (!A || !Bm || !C) return set_error(SNFFT_EINVAL, "NULL data pointer");
+    const HostLevel& L = p->host.levels[p->n];
+    cudaStream_t st = (cudaStream_t)stream;
+    for (size_t q = 0; q < L.shapes.size(); ++q) {
+        const int d = L.shapes[q].dim;
+        const int tiles = (d + MM_TILE - 1) / MM_TILE;
+        const long long nblk = (long long)B * tiles * tiles;
+        if (nblk > 0x7fffffffll) return set_error(SNFFT_ENOTSUP, "snfft_block_matmul: batch too large");
+        const size_t off = (size_t)L.coef_offsets[q] * (size_t)B;
+        dim3 grid((unsigned)nblk, 1, 1), block(MM_THREADS, 1, 1);
+        if (p->dtype == SNFFT_F32) {
+            auto kfn = block_matmul_kernel<float>;
+            SNFFT_LAUNCH(kfn, grid, block, 0, st, (const float*)A + off, (const float*)Bm + off, (float*)C + off, d, tiles);
+        } else {
+            auto kfn = block_matmul_kernel<double>;
+            SNFFT_LAUNCH(kfn, grid, block, 0, st, (const double*)A + off, (const double*)Bm + off, (double*)C + off, d, tiles);
+        }
+        g_launches.fetch_add(1);
+    }
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
+}
+
 int snfft_power(const snfft_plan_t* p, const void* F, int64_t B, void* out, void* stream) {
     if (!p) return set_error(SNFFT_EINVAL, "plan is NULL");
     if (B < 0) return set_error(SNFFT_EINVAL, "negative batch");

@@ -122,6 +122,14 @@ int snfft_inverse(const snfft_plan_t* plan, const void* F, int64_t B, void* f,
 int snfft_power(const snfft_plan_t* plan, const void* F, int64_t B, void* out, void* stream);
 
 /*
+ * Per-partition matrix products of two packed coefficient arrays (layout of snfft_forward):
+ * C_lambda[b] = A_lambda[b] . B_lambda[b] for every partition lambda and batch row b.  With A = FT(g), B = FT(f)
+ * and snfft_inverse this is the group convolution sum_sigma f(sigma) g(pi sigma^-1) (convolution theorem, reference
+ * tests/test_fourier.py:22-34, 87-109).  C must not alias A or B.
+ */
+int snfft_block_matmul(const snfft_plan_t* plan, const void* A, const void* B, void* C, int64_t batch, void* stream);
+
+/*
  * Partial forward transform over a subset of the top-level cosets
  * {sigma : sigma[i] = n-1} (the coset-sharded transform of one large function,
  * SURVEY 8e / BASELINE config 5):

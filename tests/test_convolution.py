@@ -65,3 +65,27 @@ def test_convolution_with_delta_is_translation_gpu():
     t = A.sn_convolve(f, d, n)
     assert abs(t.norm().item() / f.norm().item() - 1) < 1e-5
     assert rel_err(torch.sort(t, dim=1).values.cpu().numpy(), torch.sort(f, dim=1).values.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,B,dt,tol", [(10, 2, torch.float32, 2e-6), (9, 3, torch.float64, 1e-14), (7, 5, torch.float32, 2e-6)])
+def test_block_matmul_vs_torch_gpu(n, B, dt, tol):
+    """snfft_block_matmul (C ABI) on random packed coefficients, every partition (d up to 768: many tiles and K
+    steps, ragged edges) against torch.matmul in fp64."""
+    import math
+    from algebraist_b200 import _lib
+    from algebraist_b200.plan import get_plan
+    dev = torch.device("cuda", 0)
+    plan = get_plan(n, dt, dev)
+    nf = math.factorial(n)
+    torch.manual_seed(n)
+    a = torch.randn(B * nf, dtype=dt, device=dev)
+    b = torch.randn(B * nf, dtype=dt, device=dev)
+    c = torch.empty_like(a)
+    _lib.check(_lib.load().snfft_block_matmul(plan.handle, a.data_ptr(), b.data_ptr(), c.data_ptr(), B,
+                                              torch.cuda.current_stream(dev).cuda_stream), "snfft_block_matmul")
+    for d, off in zip(plan.dims, plan.offsets):
+        blk = slice(off * B, (off + d * d) * B)
+        want = torch.matmul(a[blk].view(B, d, d).double(), b[blk].view(B, d, d).double())
+        got = c[blk].view(B, d, d).double()
+        assert ((got - want).norm() / want.norm()).item() < tol, d
