@@ -29,6 +29,31 @@ import os
 
 from gen_base import Emitter, boffs, children, coef_off, dim, partitions, table
 
+class ScaledEmitter(Emitter):
+    """Values are (scale, name) with an arbitrary compile-time scale instead of a sign: a linear combination
+    c0 s0 N0 + c1 s1 N1 is emitted as ONE fused multiply-add  N = (c1 s1 / (c0 s0)) * N1 + N0  carrying the scale
+    c0 s0 ("fast Givens": a 2 x 2 rotation costs 2 FFMA instead of 2 FMUL + 2 FFMA), a single term costs nothing,
+    and the scales are multiplied back in where a value is stored.  Scaling by constants leaves the relative
+    rounding errors unchanged; the scales are products of at most k - 1 factors 1/d, sqrt(1 - 1/d^2), |d| <= k."""
+
+    def lin(self, terms):
+        t = [(c * v[0], v[1]) for c, v in terms if v is not None and c != 0.0]
+        if not t:
+            return None
+        s0, expr = t[0]
+        if len(t) == 1:
+            return (s0, expr)
+        for c, name in t[1:]:
+            r = c / s0
+            if r == 1.0:
+                expr = f"{expr} + {name}"
+            elif r == -1.0:
+                expr = f"{expr} - {name}"
+            else:
+                expr = f"{self.lit(r)} * {name} + {expr}"
+        return (s0, self.tmp(expr))
+
+
 LEVELS = (6, 7, 8)
 CHILD_MAJOR_MAX = 6       # levels whose tasks keep a whole child column in registers
 SPLIT_FWD = {9: 4}        # forward-only levels, generated as several headers / translation units / launches
@@ -149,7 +174,9 @@ def inverse_task(em, k, mu, i, rows, load, store):
 def value_expr(v):
     if v is None:
         return "T(0)"
-    return v[1] if v[0] == 1.0 else f"-{v[1]}"
+    if v[0] == 1.0:
+        return v[1]
+    return f"-{v[1]}" if v[0] == -1.0 else f"{Emitter.lit(v[0])} * {v[1]}"
 
 
 def row_sets(k, part):
@@ -179,7 +206,7 @@ def gen_level(k, inverse, only=None):
         if not inverse and k <= CHILD_MAJOR_MAX:
             # child-major: one task per mu; the k * d_mu inputs of the column are loaded once and stay in registers
             # for every parent lambda (k * d_mu <= 36 values at k = 6)
-            em = Emitter()
+            em = ScaledEmitter()
             cache = {}
 
             def load(r, i, em=em, cache=cache, dm=dm):
@@ -210,7 +237,7 @@ def gen_level(k, inverse, only=None):
         elif inverse and k <= CHILD_MAJOR_MAX:
             # one task per mu: the columns of the parents (sum of d_lambda = k * d_mu values) are loaded once and
             # shared by the k cosets
-            em = Emitter()
+            em = ScaledEmitter()
             cache = {}
 
             def load(lam, t, bo, em=em, cache=cache):
@@ -242,7 +269,7 @@ def gen_level(k, inverse, only=None):
                 b = children(lam).index(mu)
                 bo, dl = boffs(lam)[b], dim(lam)
                 for rows in row_sets(k, lam):
-                    em = Emitter()
+                    em = ScaledEmitter()
                     cache = {}
 
                     def load(r, i, em=em, cache=cache, dm=dm):
@@ -266,7 +293,7 @@ def gen_level(k, inverse, only=None):
             # F_lambda (the same in every chain) live throughout and spill
             for rows in row_sets(7, mu):                 # all rows of mu: the block of mu in F_lambda is then read once
                 for i in range(k):
-                    em = Emitter()
+                    em = ScaledEmitter()
 
                     def load(lam, t, bo, em=em):
                         return em.tmp(f"in[(size_t){coef_off(lam) + t * dim(lam) + bo} * s]")

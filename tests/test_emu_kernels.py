@@ -71,7 +71,9 @@ def test_fused_base_kernel_equals_level_kernels(emu, dt, B):
         fused = abi.forward(plan, f)
         emu.snfft_debug_disable_base(1)
         plain = abi.forward(plan, f)
-        assert np.array_equal(fused, plain)              # same arithmetic in the same order
+        # the column kernels carry compile-time scales through the rotations (one FMA per rotation output) and
+        # multiply them back at the stores: same numbers up to the rounding order
+        assert rel_err(fused, plain) < (1e-14 if dt == "f64" else 2e-6)
         inv_plain = abi.inverse(plan, fused, B)
         emu.snfft_debug_disable_base(0)
         inv_fused = abi.inverse(plan, fused, B)
