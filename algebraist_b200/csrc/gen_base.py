@@ -182,6 +182,36 @@ class Emitter:
         return self.lin([(1.0, v) for v in terms])
 
 
+class ScaledEmitter(Emitter):
+    """Values are (scale, name) with an arbitrary compile-time scale instead of a sign: a linear combination
+    c0 s0 N0 + c1 s1 N1 is emitted as ONE fused multiply-add  N = (c1 s1 / (c0 s0)) * N1 + N0  carrying the scale
+    c0 s0 ("fast Givens": a 2 x 2 rotation costs 2 FFMA instead of 2 FMUL + 2 FFMA), a single term costs nothing,
+    and the scales are multiplied back in where a value is stored.  Scaling by constants leaves the relative
+    rounding errors unchanged; the scales are products of at most k - 1 factors 1/d, sqrt(1 - 1/d^2), |d| <= k."""
+
+    def lin(self, terms):
+        t = [(c * v[0], v[1]) for c, v in terms if v is not None and c != 0.0]
+        if not t:
+            return None
+        s0, expr = t[0]
+        if len(t) == 1:
+            return (s0, expr)
+        for c, name in t[1:]:
+            r = c / s0
+            if r == 1.0:
+                expr = f"{expr} + {name}"
+            elif r == -1.0:
+                expr = f"{expr} - {name}"
+            else:
+                expr = f"{self.lit(r)} * {name} + {expr}"
+        return (s0, self.tmp(expr))
+
+
+def as_value(v):
+    """A loader may return a plain name or an already scaled value."""
+    return v if isinstance(v, tuple) else (1.0, v)
+
+
 def forward_column(em, k, lam, b, c, load, store):
     """F_lam[:, boff + c] = sum_i rho(s_i)..rho(s_{k-2}) embed_b(F^(i)_mu[:, c])  (fourier.py:253-273)."""
     mu = children(lam)[b]
@@ -190,7 +220,7 @@ def forward_column(em, k, lam, b, c, load, store):
     for i in range(k):
         x = [None] * dl
         for r in range(dm):
-            x[bo + r] = (1.0, load(mu, r, c, i))
+            x[bo + r] = as_value(load(mu, r, c, i))
         for j in range(k - 2, i - 1, -1):
             em.sweep(lam, j, x)
         for t in range(dl):
@@ -220,7 +250,7 @@ def inverse_column(em, k, mu, c, i, load, store):
         need.reverse()                      # need[0] = rows to load, need[m] = rows needed after m sweeps
         x = [None] * dl
         for t in sorted(need[0]):
-            x[t] = (1.0, load(lam, t, bo + c))
+            x[t] = as_value(load(lam, t, bo + c))
         for m, j in enumerate(range(i, k - 1)):
             em.sweep(lam, j, x)
             for t in range(dl):
@@ -237,14 +267,16 @@ def inverse_column(em, k, mu, c, i, load, store):
 def value_expr(v):
     if v is None:
         return "T(0)"
-    return v[1] if v[0] == 1.0 else f"-{v[1]}"
+    if v[0] == 1.0:
+        return v[1]
+    return f"-{v[1]}" if v[0] == -1.0 else f"{Emitter.lit(v[0])} * {v[1]}"
 
 
 def gen_s5(forward):
     """Levels 2..5 of one S_5 instance on 120 register values.
     x[p], p = chain index (p_1 = sum_k i_k 120/k!), y[e], e = packed S_5 coefficient index."""
     K0 = 5
-    em = Emitter()
+    em = ScaledEmitter()
     if forward:
         cur = {((1,), 0, 0, p): f"x[{p}]" for p in range(120)}
         for k in range(2, K0 + 1):
@@ -263,18 +295,13 @@ def gen_s5(forward):
                             forward_column(em, k, lam, b, c, load, store)
             # materialise signs so that the next level sees plain names
             cur = {}
-            for key, v in nxt.items():
-                if v is None:
-                    cur[key] = em.tmp("T(0)")
-                elif v[0] == 1.0:
-                    cur[key] = v[1]
-                else:
-                    cur[key] = em.tmp(f"-{v[1]}")
+            for key, v in nxt.items():          # the scales travel to the next level with the values
+                cur[key] = (1.0, em.tmp("T(0)")) if v is None else v
         for lam in partitions(K0):
             d = dim(lam)
             for t in range(d):
                 for col in range(d):
-                    em.lines.append(f"    y[{coef_off(lam) + t * d + col}] = {cur[(lam, t, col, 0)]};")
+                    em.lines.append(f"    y[{coef_off(lam) + t * d + col}] = {value_expr(cur[(lam, t, col, 0)])};")
     else:
         cur = {}
         for lam in partitions(K0):
@@ -297,15 +324,10 @@ def gen_s5(forward):
 
                             inverse_column(em, k, mu, c, i, load, store)
             cur = {}
-            for key, v in nxt.items():
-                if v is None:
-                    cur[key] = em.tmp("T(0)")
-                elif v[0] == 1.0:
-                    cur[key] = v[1]
-                else:
-                    cur[key] = em.tmp(f"-{v[1]}")
+            for key, v in nxt.items():          # the scales travel to the next level with the values
+                cur[key] = (1.0, em.tmp("T(0)")) if v is None else v
         for p in range(120):
-            em.lines.append(f"    y[{p}] = {cur[((1,), 0, 0, p)]};")
+            em.lines.append(f"    y[{p}] = {value_expr(cur[((1,), 0, 0, p)])};")
     name = "s5_forward" if forward else "s5_inverse"
     head = [f"template <typename T>",
             f"__device__ __forceinline__ void {name}(const T (&x)[120], T (&y)[120]) {{"]
@@ -329,7 +351,7 @@ def gen_l6(forward):
             # parent lambda of mu (loading them per parent re-read each child 2.6 times from DRAM)
             mu = part
             for c in range(dim(mu)):
-                em = Emitter()
+                em = ScaledEmitter()
                 cache = {}
 
                 def load(m, r, cc, i, em=em, cache=cache):
@@ -356,7 +378,7 @@ def gen_l6(forward):
             mu = part
             for c in range(dim(mu)):
                 for i in range(k):
-                    em = Emitter()
+                    em = ScaledEmitter()
 
                     def load(l, t, col, em=em):
                         e6 = coef_off(l) + t * dim(l) + col

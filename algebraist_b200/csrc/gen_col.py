@@ -27,32 +27,7 @@ Combinatorics come from gen_base.py (same conventions, same citations).
 import math
 import os
 
-from gen_base import Emitter, boffs, children, coef_off, dim, partitions, table
-
-class ScaledEmitter(Emitter):
-    """Values are (scale, name) with an arbitrary compile-time scale instead of a sign: a linear combination
-    c0 s0 N0 + c1 s1 N1 is emitted as ONE fused multiply-add  N = (c1 s1 / (c0 s0)) * N1 + N0  carrying the scale
-    c0 s0 ("fast Givens": a 2 x 2 rotation costs 2 FFMA instead of 2 FMUL + 2 FFMA), a single term costs nothing,
-    and the scales are multiplied back in where a value is stored.  Scaling by constants leaves the relative
-    rounding errors unchanged; the scales are products of at most k - 1 factors 1/d, sqrt(1 - 1/d^2), |d| <= k."""
-
-    def lin(self, terms):
-        t = [(c * v[0], v[1]) for c, v in terms if v is not None and c != 0.0]
-        if not t:
-            return None
-        s0, expr = t[0]
-        if len(t) == 1:
-            return (s0, expr)
-        for c, name in t[1:]:
-            r = c / s0
-            if r == 1.0:
-                expr = f"{expr} + {name}"
-            elif r == -1.0:
-                expr = f"{expr} - {name}"
-            else:
-                expr = f"{self.lit(r)} * {name} + {expr}"
-        return (s0, self.tmp(expr))
-
+from gen_base import Emitter, ScaledEmitter, boffs, children, coef_off, dim, partitions, table
 
 LEVELS = (6, 7, 8)
 CHILD_MAJOR_MAX = 6       # levels whose tasks keep a whole child column in registers
