@@ -44,6 +44,7 @@ constexpr int COL_MAXGROUPS = 24;
 
 struct ColGroups {
     int ngroups, chunk;
+    unsigned long long total;             // blocks of the launch (must fit a 31-bit grid)
     unsigned blk0[COL_MAXGROUPS + 1];     // first block of each group
     int task0[COL_MAXGROUPS], ntask[COL_MAXGROUPS], dmu[COL_MAXGROUPS];
 };
@@ -65,6 +66,7 @@ inline ColGroups col_groups(long long ninst, int chunk) {
         blk += (unsigned long long)tiles * g.ntask[i];
     }
     for (int i = I::ngroups; i <= COL_MAXGROUPS; ++i) g.blk0[i] = (unsigned)blk;
+    g.total = blk;
     return g;
 }
 

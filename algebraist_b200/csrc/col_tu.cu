@@ -51,9 +51,10 @@ extern "C" int COL_NAME(const void* in, void* out, long long ninst, cudaStream_t
         return SNFFT_COL_K == 9 ? 4 : (SNFFT_COL_K == 8 ? (SNFFT_COL_F64 ? 8 : 16) : (SNFFT_COL_K == 7 && SNFFT_COL_INV ? 74 : 148));
     }();
     const ColGroups g = col_groups<SNFFT_COL_K, SNFFT_COL_INV != 0>(ninst, chunk);
-    const unsigned nblk = g.blk0[g.ngroups];
+    // the kernels use a 32-bit row stride and a one-dimensional grid
+    if (ninst >= (1ll << 32) || g.total > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    const unsigned nblk = (unsigned)g.total;
     if (nblk == 0) return 0;
-    if (ninst >= (1ll << 32)) return (int)cudaErrorInvalidValue;     // the kernels use a 32-bit row stride
     dim3 grid(nblk, 1, 1), block(COL_THREADS, 1, 1);
     auto kfn = col_kernel<col_t, SNFFT_COL_K, SNFFT_COL_INV != 0>;
     SNFFT_LAUNCH(kfn, grid, block, 0, st, (const col_t*)in, (col_t*)out, ninst, g);
