@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r01r.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_r01r.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r01r.log 2>&1; echo "smoke rc=$?"
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r01r.json 2> gpurun_out/bench_r01r.err; echo "bench rc=$?"
+timeout 170 ncu --set full --clock-control none --kernel-name-base demangled -k 'regex:col_kernel|s5_kernel' -f -o /tmp/prof_col python tools/prof_step.py --n 10 --batch 128 > gpurun_out/ncu_col_r01r.log 2>&1; echo "ncu rc=$?"
+python tools/ncu_summary.py /tmp/prof_col.ncu-rep gpurun_out/ncu_col_r01r.csv > /dev/null; echo "summary rc=$?"
