@@ -26,6 +26,13 @@ def col_deps(k):
 
 
 
+def tz_deps(kind):
+    gen = "tz_gen_z7.cuh" if kind == 0 else f"tz_gen_t{kind}.cuh"
+    return [os.path.join(CSRC, f) for f in ("tz_tu.cu", "tz_kernels.cuh", "tz_gen_tab.cuh", gen)]
+
+
+# top / bottom kernels (csrc/tz_tu.cu): kind 0 = Z kernel, 9 / 10 = T kernel of that level
+TZ_COMBOS = [(kind, f64, inv) for kind in (0, 9, 10) for f64 in (0, 1) for inv in (0, 1)]
 COL_COMBOS = [(k, f64, inv) for k in (6, 7, 8) for f64 in (0, 1) for inv in (0, 1)]
 COL9_PARTS = 4        # level 9, forward only: gen_col.SPLIT_FWD
 # threads per CTA of the column kernels by (level, fp64); default 128.  One large CTA per SM keeps all its warps on
@@ -47,6 +54,9 @@ def units():
            f"-DSNFFT_COL_THREADS={COL_THREADS.get((9, f64), 128)}"],
           [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", f"col_gen_9p{p}.cuh")])
          for f64 in (0, 1) for p in range(COL9_PARTS)] + u
+    u += [(os.path.join(OBJ, f"tz_{kind}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "tz_tu.cu"),
+           [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"], tz_deps(kind))
+          for kind, f64, inv in TZ_COMBOS]
     u.insert(0, (os.path.join(OBJ, "snfft.o"), os.path.join(CSRC, "snfft.cu"), [], MAIN_DEPS))
     u.append((os.path.join(OBJ, "plan.o"), os.path.join(CSRC, "plan.cpp"), [], PLAN_DEPS))
     return u
@@ -54,16 +64,23 @@ def units():
 
 def generate_col_headers(force: bool = False):
     """col_gen_<k>.cuh (20 MB of straight-line code) are not kept in git: csrc/gen_col.py writes them (2 s)."""
-    gens = [os.path.join(CSRC, f) for f in ("gen_col.py", "gen_base.py")]
-    heads = [os.path.join(CSRC, f"col_gen_{k}.cuh") for k in (6, 7, 8)] + [
-        os.path.join(CSRC, f"col_gen_9p{p}.cuh") for p in range(COL9_PARTS)]
-    if force or any(stale(h, gens) for h in heads):
-        res = subprocess.run([sys.executable, os.path.join(CSRC, "gen_col.py")], capture_output=True, text=True, cwd=CSRC)
-        if res.returncode != 0:
-            raise RuntimeError("gen_col.py failed:\n" + res.stdout + res.stderr)
-        for h in heads:             # unchanged headers keep their contents and objects; mark them as checked
-            if os.path.getmtime(h) < max(os.path.getmtime(g) for g in gens):
-                os.utime(h)
+    for script, gen_names, head_names in (
+            ("gen_col.py", ("gen_col.py", "gen_base.py"),
+             [f"col_gen_{k}.cuh" for k in (6, 7, 8)] + [f"col_gen_9p{p}.cuh" for p in range(COL9_PARTS)]),
+            ("gen_tz.py", ("gen_tz.py", "gen_col.py", "gen_base.py"),
+             ["tz_gen_z7.cuh", "tz_gen_tab.cuh", "tz_gen_t9.cuh", "tz_gen_t10.cuh"])):
+        gens = [os.path.join(CSRC, f) for f in gen_names]
+        heads = [os.path.join(CSRC, f) for f in head_names]
+        # the generators only rewrite a header whose contents change, so an edit of a generator that leaves the
+        # code alone does not recompile anything; the stamp records that the generator ran after its last edit
+        stamp = os.path.join(OBJ, script + ".stamp")
+        if force or stale(stamp, gens) or not all(os.path.exists(h) for h in heads):
+            res = subprocess.run([sys.executable, os.path.join(CSRC, script)], capture_output=True, text=True, cwd=CSRC)
+            if res.returncode != 0:
+                raise RuntimeError(script + " failed:\n" + res.stdout + res.stderr)
+            os.makedirs(OBJ, exist_ok=True)
+            with open(stamp, "w") as fh:
+                fh.write("generated\n")
 
 
 def stale(target, deps):

@@ -100,7 +100,7 @@ def block_of(lam, t):
     raise ValueError(t)
 
 
-def inverse_task(em, k, mu, i, rows, load, store):
+def inverse_task(em, k, mu, i, rows, load, store, unit_scale=False):
     """Rows `rows` of G^(i)_mu[:, c].  The bottom sweeps s_i..s_{k-3} never leave a child block of lambda, so the
     column of F_lambda is processed one child block at a time (loads, bottom sweeps, its term of the top sweep
     s_{k-2} added to the running sums): only the sums and one block are live at any point."""
@@ -112,7 +112,7 @@ def inverse_task(em, k, mu, i, rows, load, store):
             continue
         b = ch.index(mu)
         bo, dl = boffs(lam)[b], dim(lam)
-        scale = dl / (k * dm)
+        scale = 1.0 if unit_scale else dl / (k * dm)      # unit_scale: gen_tz.py applies the weights in its T kernel
         want = [bo + r for r in rows]
         if i > k - 2:                       # coset k-1: identity
             for r in rows:

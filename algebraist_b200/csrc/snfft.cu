@@ -90,6 +90,25 @@ static int set_error(int code, const std::string& msg) {
             return set_error(SNFFT_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+// Makes `dev` the current CUDA device for a scope and restores the caller's device afterwards (plan creation and
+// the *_host entry points must not change the process-wide current device as a side effect).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (prev == dev) {
+            prev = -1;
+            ok = true;
+        } else {
+            ok = cudaSetDevice(dev) == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 static const KClass* class_table(int dtype) { return dtype == SNFFT_F32 ? kClasses32 : kClasses64; }
 
 static int pick_class(int dtype, int d) {
@@ -114,6 +133,9 @@ struct TbRange {          // one launch of the TB kernels: tasks that share a ti
 struct DevLevel {
     // column kernels (col_kernels.cuh, levels 6..8): registers only; chosen when the plan is created
     bool col_fwd = false, col_inv = false;
+    // top / bottom kernels (tz_kernels.cuh, levels 9 and 10): two streaming launches per step through the third
+    // workspace buffer; chosen when the plan is created
+    bool tz_fwd = false, tz_inv = false;
     // TB kernels (level_tb.cuh): tb_s = 0 means the level runs the sweep-per-pass kernels
     int tb_s = 0;
     int tb_inv_nbuf = 2;                      // chains per pass of the inverse TB kernel at this level
@@ -668,6 +690,73 @@ static int run_col_level(const snfft_plan* p, int k, const void* in, void* out, 
     return SNFFT_OK;
 }
 
+// Top / bottom kernels (tz_kernels.cuh / tz_tu.cu: one translation unit per kernel, dtype and direction).
+extern "C" {
+#define SNFFT_TZ_DECL(dt, dir)                                                                 \
+    int snfft_tz_z_##dt##_##dir(int, const void*, void*, long long, cudaStream_t);             \
+    int snfft_tz_z_prepare_##dt##_##dir(int);                                                  \
+    int snfft_tz_t9_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);                \
+    int snfft_tz_t10_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);
+SNFFT_TZ_DECL(f32, fwd) SNFFT_TZ_DECL(f32, inv) SNFFT_TZ_DECL(f64, fwd) SNFFT_TZ_DECL(f64, inv)
+#undef SNFFT_TZ_DECL
+}
+constexpr int kTzFirst = 9, kTzLast = 10, kTzMB = 7;
+
+// Levels that use the top / bottom kernels: automatic kernel choice only; SNFFT_TZ_FWD / SNFFT_TZ_INV (lists of
+// levels, "" = none) override when a plan is created.  They take precedence over the column kernels.
+static void tz_pick_dirs(int k, bool* fwd, bool* inv) {
+    *fwd = *inv = false;
+    if (k < kTzFirst || k > kTzLast || g_tb_mode.load() != -1) return;
+    *fwd = tb_level_listed("SNFFT_TZ_FWD", k, true);
+    *inv = tb_level_listed("SNFFT_TZ_INV", k, true);
+}
+
+static int tz_prepare(int dtype, int k, bool fwd, bool inv) {
+    int rc = 0;
+    if (fwd) rc = dtype == SNFFT_F32 ? snfft_tz_z_prepare_f32_fwd(k) : snfft_tz_z_prepare_f64_fwd(k);
+    if (!rc && inv) rc = dtype == SNFFT_F32 ? snfft_tz_z_prepare_f32_inv(k) : snfft_tz_z_prepare_f64_inv(k);
+    if (rc) return set_error(SNFFT_ECUDA, std::string("top/bottom kernel tables: ") + cudaGetErrorString((cudaError_t)rc));
+    return SNFFT_OK;
+}
+
+// One level step through the top / bottom kernels.  forward: in = X_{k-1}, out = X_k; inverse: in = X_k,
+// out = X_{k-1}; z = the third workspace buffer (MB/k of a level array is used).
+// Profile records: kernel_class -4 = Z kernel, -5 = T kernel.
+template <typename T, bool INVERSE>
+static int run_tz_level(const snfft_plan* p, int k, const void* in, void* out, void* z, long long B, cudaStream_t st) {
+    const long long ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
+    const long long fk = p->host.factorial[k];
+    int rc;
+    auto fail = [](int e) { return set_error(SNFFT_ECUDA, std::string("top/bottom kernel launch: ") + cudaGetErrorString((cudaError_t)e)); };
+    constexpr bool F32 = sizeof(T) == 4;
+    if (!INVERSE) {
+        {
+            ProfScope prof(p, st, 0, k, -4, fk * kTzMB / k);
+            rc = F32 ? snfft_tz_z_f32_fwd(k, in, z, ninst, st) : snfft_tz_z_f64_fwd(k, in, z, ninst, st);
+            g_launches.fetch_add(1);
+            if (rc) return fail(rc);
+        }
+        ProfScope prof(p, st, 0, k, -5, fk);
+        if (k == 9) rc = F32 ? snfft_tz_t9_f32_fwd(z, (void*)in, out, ninst, st) : snfft_tz_t9_f64_fwd(z, (void*)in, out, ninst, st);
+        else rc = F32 ? snfft_tz_t10_f32_fwd(z, (void*)in, out, ninst, st) : snfft_tz_t10_f64_fwd(z, (void*)in, out, ninst, st);
+        g_launches.fetch_add(1);
+        if (rc) return fail(rc);
+    } else {
+        {
+            ProfScope prof(p, st, 1, k, -5, fk);
+            if (k == 9) rc = F32 ? snfft_tz_t9_f32_inv(z, out, (void*)in, ninst, st) : snfft_tz_t9_f64_inv(z, out, (void*)in, ninst, st);
+            else rc = F32 ? snfft_tz_t10_f32_inv(z, out, (void*)in, ninst, st) : snfft_tz_t10_f64_inv(z, out, (void*)in, ninst, st);
+            g_launches.fetch_add(1);
+            if (rc) return fail(rc);
+        }
+        ProfScope prof(p, st, 1, k, -4, fk * kTzMB / k);
+        rc = F32 ? snfft_tz_z_f32_inv(k, z, out, ninst, st) : snfft_tz_z_f64_inv(k, z, out, ninst, st);
+        g_launches.fetch_add(1);
+        if (rc) return fail(rc);
+    }
+    return SNFFT_OK;
+}
+
 static IndexArgs make_index_args(int n);
 
 // levels 1..n of the forward pipeline; *result points at X_n (instance fastest) inside the workspace
@@ -676,6 +765,7 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
     const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
     void* cur = ws;
     void* nxt = (char*)ws + half;
+    void* zbuf = (char*)ws + 2 * half;          // third buffer: only when the plan has top / bottom levels
     int rc;
     if ((rc = run_gather<T, false>(p, f, cur, B, st))) return rc;
     int k_first = 2;
@@ -695,7 +785,8 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
         k_first = kBaseK0 + 1;
     }
     for (int k = k_first; k <= p->n; ++k) {
-        if (base == 0 && p->lev[k].col_fwd) rc = run_col_level<T, false>(p, k, cur, nxt, B, st);
+        if (base == 0 && p->lev[k].tz_fwd) rc = run_tz_level<T, false>(p, k, cur, nxt, zbuf, B, st);
+        else if (base == 0 && p->lev[k].col_fwd) rc = run_col_level<T, false>(p, k, cur, nxt, B, st);
         else if (p->lev[k].tb_s > 0 && p->lev[k].tb_fwd) rc = run_tb_level<T, false>(p, k, cur, nxt, B, st);
         else rc = run_fwd_level<T>(p, k, cur, nxt, B, st);
         if (rc) return rc;
@@ -752,6 +843,7 @@ template <typename T>
 static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f, void* ws, cudaStream_t st) {
     const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
     void* bufs[2] = {ws, (char*)ws + half};
+    void* zbuf = (char*)ws + 2 * half;
     int which = 1, rc;
     if ((rc = run_pack<T, false>(p, F, bufs[0], B, st))) return rc;
     const void* cur = bufs[0];
@@ -760,7 +852,8 @@ static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f
     if (base == 0 && p->n > 5) k_last = p->n > 6 ? 7 : 6;
     else if (base == 2 && p->n > kBaseK0) k_last = kBaseK0 + 1;
     for (int k = p->n; k >= k_last; --k) {
-        if (base == 0 && p->lev[k].col_inv) rc = run_col_level<T, true>(p, k, cur, bufs[which], B, st);
+        if (base == 0 && p->lev[k].tz_inv) rc = run_tz_level<T, true>(p, k, cur, bufs[which], zbuf, B, st);
+        else if (base == 0 && p->lev[k].col_inv) rc = run_col_level<T, true>(p, k, cur, bufs[which], B, st);
         else if (p->lev[k].tb_s > 0 && p->lev[k].tb_inv) rc = run_tb_level<T, true>(p, k, cur, bufs[which], B, st);
         else rc = run_inv_level<T>(p, k, cur, bufs[which], B, st);
         if (rc) return rc;
@@ -868,8 +961,9 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
     if (n < 2 || n > SNFFT_MAX_N) return set_error(SNFFT_EINVAL, "n must be in [2, 12]");
     if (dtype != SNFFT_F32 && dtype != SNFFT_F64) return set_error(SNFFT_EINVAL, "dtype must be 0 (f32) or 1 (f64)");
     snfft_plan* p = nullptr;
+    DeviceGuard guard(device);          // the caller's current device is restored on every exit path
+    if (!guard.ok) return set_error(SNFFT_ECUDA, "cudaSetDevice failed");
     try {
-        SNFFT_CUDA(cudaSetDevice(device));
         p = new snfft_plan();
         p->n = n;
         p->dtype = dtype;
@@ -927,6 +1021,8 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
         for (int k = 2; k <= n; ++k) {
             int rc = dtype == SNFFT_F32 ? build_level<float>(p, k) : build_level<double>(p, k);
             col_pick_dirs(k, &p->lev[k].col_fwd, &p->lev[k].col_inv);
+            tz_pick_dirs(k, &p->lev[k].tz_fwd, &p->lev[k].tz_inv);
+            if (!rc) rc = tz_prepare(dtype, k, p->lev[k].tz_fwd, p->lev[k].tz_inv);
             const int s = tb_pick_s(k);
             if (!rc && s > 0 && k - s >= 3) {
                 rc = dtype == SNFFT_F32 ? build_tb_level<float>(p, k, s) : build_tb_level<double>(p, k, s);
@@ -1002,7 +1098,8 @@ int snfft_plan_yor_table(const snfft_plan_t* p, int k, int part, int j, int* d, 
 
 size_t snfft_workspace_bytes(const snfft_plan_t* p, int64_t B) {
     if (!p || B < 0) return 0;
-    return 2 * (size_t)B * (size_t)p->host.factorial[p->n] * p->esize;
+    // two ping-pong level arrays, plus the intermediate array of the top / bottom kernels when a level uses them
+    return (p->n >= kTzFirst ? 3 : 2) * (size_t)B * (size_t)p->host.factorial[p->n] * p->esize;
 }
 
 static int check_io(const snfft_plan_t* p, const void* a, const void* b, int64_t B, const void* ws, size_t ws_bytes) {
@@ -1138,7 +1235,8 @@ static int host_call(snfft_plan_t* p, const void* in, int64_t B, void* out, void
     if (B < 0) return set_error(SNFFT_EINVAL, "negative batch");
     if (B == 0) return SNFFT_OK;
     if (!in || !out) return set_error(SNFFT_EINVAL, "NULL data pointer");
-    SNFFT_CUDA(cudaSetDevice(p->device));
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return set_error(SNFFT_ECUDA, "cudaSetDevice failed");
     int rc = host_scratch(p, B);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;

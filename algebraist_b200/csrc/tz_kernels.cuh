@@ -1,0 +1,147 @@
+// "Top / bottom" kernels of the level steps k = 9, 10 (generated code tz_gen_*.cuh, gen_tz.py has the derivation
+// and the reference citations).  A level step (fourier.py:253-273, inverse fourier.py:191-199) is split in two
+// streaming kernels with an intermediate array Z of MB/k of the level's size (MB = 7):
+//   forward:  X_{k-1} --Z kernel (level-7 column operators on pieces of the inputs, summed over the cosets i < 7)--> Z
+//             Z, X_{k-1}[cosets i >= 7] --T kernel (top sweeps s_6 .. s_{k-2} as one small map per (mu, alpha))--> X_k
+//   inverse:  X_k --T' kernel--> Z', X_{k-1}[cosets i >= 7];   Z' --Z' kernel--> X_{k-1}[cosets i < 7]
+// No shared memory, no barriers, no tables in the inner code: the Young's-orthogonal-form coefficients
+// (irreps.py:91-109) are FFMA immediates of straight-line code, lanes run over consecutive instances so every
+// global access is a contiguous run, every element of X_{k-1}, Z and X_k moves once per kernel that needs it.
+//
+// One translation unit per (kind, dtype, direction): SNFFT_TZ_KIND = 0 (Z kernel, shared by all levels) or the
+// level k of a T kernel.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#ifndef SNFFT_TZ_KIND
+#error "tz_kernels.cuh: define SNFFT_TZ_KIND (0 = Z kernel, 9 / 10 = T kernel of that level)"
+#endif
+#include "tz_gen_tab.cuh"
+#if SNFFT_TZ_KIND == 0
+#include "tz_gen_z7.cuh"
+#elif SNFFT_TZ_KIND == 9
+#include "tz_gen_t9.cuh"
+#elif SNFFT_TZ_KIND == 10
+#include "tz_gen_t10.cuh"
+#endif
+
+namespace snfft {
+namespace {
+
+constexpr int TZ_MB = 7;
+constexpr int Z_THREADS = 128;
+constexpr int T_THREADS = 256;
+constexpr int Z_MAXGROUPS = 11;          // partitions of MB - 1 = 6
+constexpr int T_MAXTASKS = 256;
+
+// ---- Z kernel --------------------------------------------------------------------------------------------
+// A group is a shape zeta of S_6; its tasks are the parents alpha (forward) or the cosets i < 7 (inverse); its
+// lanes are (segment, column c, instance): a segment is one piece (mu, path mu -> zeta) of level k-1.  Block
+// order inside a group as in col_kernels.cuh: `chunk` tiles of one task, then the same tiles of the next task,
+// so that the sibling tasks re-read their inputs from L2 while the CTAs of an SM share code.
+struct ZSeg {
+    int ustart;            // first unit (segment, c) of this segment inside its group
+    int dmu;
+    int in_off;            // (coef_off(mu) + off d_mu) k     : element offset / NINST_k of row 0, column 0, coset 0 in X_{k-1}
+    int z_off;             // MB (coef_off(mu) + off d_mu)    : the same in Z
+};
+struct ZGroups {
+    int ngroups, chunk, k;
+    unsigned blk0[Z_MAXGROUPS + 1];
+    int task0[Z_MAXGROUPS], ntask[Z_MAXGROUPS];
+    unsigned ubase[Z_MAXGROUPS];                 // first entry of the group in unit2seg
+    unsigned long long lanes[Z_MAXGROUPS];       // units of the group * NINST_k
+};
+
+#if SNFFT_TZ_KIND == 0
+template <typename T, bool INV>
+__global__ void __launch_bounds__(Z_THREADS, (sizeof(T) == 4 ? 640 : 384) / Z_THREADS)
+z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, const ZGroups g, const ZSeg* __restrict__ segs,
+         const unsigned* __restrict__ unit2seg) {
+    const unsigned b = blockIdx.x;
+    int gi = 0;
+    while (gi + 1 < g.ngroups && b >= g.blk0[gi + 1]) ++gi;
+    const unsigned local = b - g.blk0[gi];
+    const unsigned nt = (unsigned)g.ntask[gi];
+    const unsigned long long qn = g.lanes[gi];
+    const unsigned ntiles = (unsigned)((qn + Z_THREADS - 1) / Z_THREADS);
+    const unsigned per = (unsigned)g.chunk * nt;
+    const unsigned ch = local / per, r = local - ch * per;
+    const unsigned left = ntiles - ch * (unsigned)g.chunk;
+    const unsigned cht = left < (unsigned)g.chunk ? left : (unsigned)g.chunk;
+    const unsigned tk = r / cht;
+    const unsigned tile = ch * (unsigned)g.chunk + (r - tk * cht);
+    const int task = g.task0[gi] + (int)tk;
+    const unsigned long long q = (unsigned long long)tile * Z_THREADS + threadIdx.x;
+    if (q >= qn) return;
+    unsigned u, inst;
+    if ((q >> 32) == 0) {
+        u = (unsigned)q / s;
+        inst = (unsigned)q - u * s;
+    } else {
+        u = (unsigned)(q / s);
+        inst = (unsigned)(q - (unsigned long long)u * s);
+    }
+    const ZSeg sg = segs[unit2seg[g.ubase[gi] + u]];
+    const unsigned c = u - (unsigned)sg.ustart;
+    const size_t xo = ((size_t)sg.in_off + (size_t)c * (unsigned)g.k) * s + inst;
+    const size_t zo = ((size_t)sg.z_off + c) * s + inst;
+    const unsigned rs = (unsigned)sg.dmu * (unsigned)g.k * s, zs = (unsigned)sg.dmu * s;
+    if constexpr (!INV) zb7f_run<T>(task, src + xo, dst + zo, rs, s, zs);
+    else zb7i_run<T>(task, src + zo, dst + xo, rs, s, zs);
+}
+#endif
+
+// ---- T kernel --------------------------------------------------------------------------------------------
+// A task is (mu of k-1, alpha of 7); a thread is (row r of alpha, column c of mu, instance).
+struct TTasks {
+    int ntasks;
+    unsigned blk0[T_MAXTASKS + 1];
+    unsigned short dal[T_MAXTASKS], dmu[T_MAXTASKS];
+};
+
+#if SNFFT_TZ_KIND != 0
+template <typename T, int K, bool INV>
+__global__ void __launch_bounds__(T_THREADS, 2)
+t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::conditional<INV, T*, const T*>::type xb,
+         typename std::conditional<INV, const T*, T*>::type lb, unsigned s, const TTasks g) {
+    const unsigned b = blockIdx.x;
+    int lo = 0, hi = g.ntasks - 1;               // last task with blk0 <= b
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (g.blk0[mid] <= b) lo = mid;
+        else hi = mid - 1;
+    }
+    const int task = lo;
+    const unsigned dmu = g.dmu[task];
+    const unsigned long long qn = (unsigned long long)g.dal[task] * dmu * s;
+    const unsigned long long q = (unsigned long long)(b - g.blk0[task]) * T_THREADS + threadIdx.x;
+    if (q >= qn) return;
+    unsigned rc, inst;
+    if ((q >> 32) == 0) {
+        rc = (unsigned)q / s;
+        inst = (unsigned)q - rc * s;
+    } else {
+        rc = (unsigned)(q / s);
+        inst = (unsigned)(q - (unsigned long long)rc * s);
+    }
+    const unsigned r = rc / dmu, c = rc - r * dmu;
+    if constexpr (K == 9) {
+#if SNFFT_TZ_KIND == 9
+        if constexpr (!INV) tz9f_run<T>(task, zb + inst, xb + inst, lb + inst, r, c, s);
+        else tz9i_run<T>(task, zb + inst, xb + inst, lb + inst, r, c, s);
+#endif
+    } else {
+#if SNFFT_TZ_KIND == 10
+        if constexpr (!INV) tz10f_run<T>(task, zb + inst, xb + inst, lb + inst, r, c, s);
+        else tz10i_run<T>(task, zb + inst, xb + inst, lb + inst, r, c, s);
+#endif
+    }
+}
+#endif
+
+}  // namespace
+}  // namespace snfft

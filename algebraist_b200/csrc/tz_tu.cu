@@ -1,0 +1,187 @@
+// One translation unit per (kind, dtype, direction) of the top / bottom kernels (tz_kernels.cuh):
+//   -DSNFFT_TZ_KIND=0      Z kernel (level-7 column operators with run-time strides), every level
+//   -DSNFFT_TZ_KIND=9|10   T kernel of that level
+//   -DSNFFT_TZ_F64=0|1  -DSNFFT_TZ_INV=0|1
+// Exports (0 or a cudaError_t):
+//   int snfft_tz_z_<f32|f64>_<fwd|inv>(int k, const void* src, void* dst, long long ninst, stream)
+//        forward: src = X_{k-1}, dst = Z;  inverse: src = Z', dst = X_{k-1}
+//   int snfft_tz_z_prepare_<f32|f64>_<fwd|inv>(int k)        uploads the level's segment tables to the current device
+//   int snfft_tz_t<k>_<f32|f64>_<fwd|inv>(void* z, void* x, void* xk, long long ninst, stream)
+//        forward: reads z, x (= X_{k-1}), writes xk (= X_k);  inverse: reads xk, writes z and the cosets i >= 7 of x
+#ifdef SNFFT_HOST_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <type_traits>
+#include <vector>
+
+#include "tz_kernels.cuh"
+
+#if SNFFT_TZ_F64
+typedef double tz_t;
+#define TZ_DT f64
+#else
+typedef float tz_t;
+#define TZ_DT f32
+#endif
+#if SNFFT_TZ_INV
+#define TZ_DIR inv
+#else
+#define TZ_DIR fwd
+#endif
+#define TZ_CAT3_(a, b, c) a##b##_##c
+#define TZ_CAT3(a, b, c) TZ_CAT3_(a, b, c)
+
+namespace {
+using namespace snfft;
+
+#if SNFFT_TZ_KIND == 0
+constexpr int kMaxDev = 64;
+struct ZDev {                      // device copy of one level's segment tables
+    ZSeg* segs = nullptr;
+    unsigned* unit2seg = nullptr;
+    unsigned ubase[Z_MAXGROUPS] = {};
+    unsigned units[Z_MAXGROUPS] = {};
+    bool ready = false;
+};
+ZDev g_zdev[kMaxDev][2];           // [device][k - 9]
+std::mutex g_zmu;
+
+template <int K>
+int z_upload(ZDev& d) {
+    using L = TzLevel<K>;
+    std::vector<ZSeg> segs(L::nsegs);
+    std::vector<unsigned> u2s;
+    int g_prev = -1;
+    unsigned ustart = 0;
+    for (int i = 0; i < Z_MAXGROUPS; ++i) d.ubase[i] = d.units[i] = 0;
+    for (int i = 0; i < L::nsegs; ++i) {
+        const int g = L::seg_group()[i];
+        if (g != g_prev) {          // segments are sorted by group
+            d.ubase[g] = (unsigned)u2s.size();
+            ustart = 0;
+            g_prev = g;
+        }
+        segs[i].ustart = (int)ustart;
+        segs[i].dmu = L::seg_dmu()[i];
+        segs[i].in_off = L::seg_in()[i];
+        segs[i].z_off = L::seg_z()[i];
+        for (int c = 0; c < segs[i].dmu; ++c) u2s.push_back((unsigned)i);
+        ustart += (unsigned)segs[i].dmu;
+        d.units[g] = ustart;
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&d.segs, segs.size() * sizeof(ZSeg))) != cudaSuccess) return (int)e;
+    if ((e = cudaMalloc((void**)&d.unit2seg, u2s.size() * sizeof(unsigned))) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpy(d.segs, segs.data(), segs.size() * sizeof(ZSeg), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpy(d.unit2seg, u2s.data(), u2s.size() * sizeof(unsigned), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    d.ready = true;
+    return 0;
+}
+
+int z_tables(int k, ZDev** out) {
+    if (k != 9 && k != 10) return (int)cudaErrorInvalidValue;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= kMaxDev) return (int)cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lock(g_zmu);
+    ZDev& d = g_zdev[dev][k - 9];
+    if (!d.ready) {
+        const int rc = k == 9 ? z_upload<9>(d) : z_upload<10>(d);
+        if (rc) return rc;
+    }
+    *out = &d;
+    return 0;
+}
+#endif
+
+}  // namespace
+
+#if SNFFT_TZ_KIND == 0
+
+#define TZ_ZNAME TZ_CAT3(snfft_tz_z_, TZ_DT, TZ_DIR)
+#define TZ_ZPREP TZ_CAT3(snfft_tz_z_prepare_, TZ_DT, TZ_DIR)
+
+extern "C" int TZ_ZPREP(int k) {
+    ZDev* d = nullptr;
+    return z_tables(k, &d);
+}
+
+extern "C" int TZ_ZNAME(int k, const void* src, void* dst, long long ninst, cudaStream_t st) {
+    using namespace snfft;
+    static const int chunk = [] {
+        // tiles of one task that run before the next task of its group (see col_kernels.cuh); SNFFT_TZ_CHUNK overrides
+        const char* e = std::getenv("SNFFT_TZ_CHUNK");
+        return e ? std::atoi(e) : (SNFFT_TZ_INV ? 74 : 148);
+    }();
+    ZDev* d = nullptr;
+    int rc = z_tables(k, &d);
+    if (rc) return rc;
+    using I = ZInfo<SNFFT_TZ_INV != 0>;
+    static_assert(I::ngroups <= Z_MAXGROUPS, "too many groups");
+    // 32-bit strides: row stride d_mu k NINST of X_{k-1} (d_mu <= 216 at k = 10)
+    if (ninst <= 0 || (unsigned long long)ninst * 216ull * (unsigned long long)k >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    ZGroups g;
+    g.ngroups = I::ngroups;
+    g.chunk = chunk < 1 ? 1 : chunk;
+    g.k = k;
+    unsigned long long blk = 0;
+    for (int i = 0; i < I::ngroups; ++i) {
+        g.blk0[i] = (unsigned)blk;
+        g.task0[i] = I::task0()[i];
+        g.ntask[i] = I::ntask()[i];
+        g.ubase[i] = d->ubase[i];
+        g.lanes[i] = (unsigned long long)d->units[i] * (unsigned long long)ninst;
+        blk += ((g.lanes[i] + Z_THREADS - 1) / Z_THREADS) * (unsigned long long)g.ntask[i];
+    }
+    g.blk0[I::ngroups] = (unsigned)blk;
+    if (blk > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    if (blk == 0) return 0;
+    dim3 grid((unsigned)blk, 1, 1), block(Z_THREADS, 1, 1);
+    auto kfn = z_kernel<tz_t, SNFFT_TZ_INV != 0>;
+    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const tz_t*)src, (tz_t*)dst, (unsigned)ninst, g, (const ZSeg*)d->segs,
+                 (const unsigned*)d->unit2seg);
+    return (int)cudaGetLastError();
+}
+
+#else
+
+#define TZ_TNAME_(k, dt, dir) snfft_tz_t##k##_##dt##_##dir
+#define TZ_TNAME__(k, dt, dir) TZ_TNAME_(k, dt, dir)
+#define TZ_TNAME TZ_TNAME__(SNFFT_TZ_KIND, TZ_DT, TZ_DIR)
+
+extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_t st) {
+    using namespace snfft;
+    using L = TzLevel<SNFFT_TZ_KIND>;
+    static_assert(L::ntasks <= T_MAXTASKS, "too many T tasks");
+    if (ninst <= 0 || ninst >= (1ll << 32)) return (int)cudaErrorInvalidValue;
+    TTasks g;
+    g.ntasks = L::ntasks;
+    unsigned long long blk = 0;
+    for (int t = 0; t < L::ntasks; ++t) {
+        g.blk0[t] = (unsigned)blk;
+        g.dal[t] = (unsigned short)L::t_dal()[t];
+        g.dmu[t] = (unsigned short)L::t_dmu()[t];
+        const unsigned long long q = (unsigned long long)L::t_dal()[t] * L::t_dmu()[t] * (unsigned long long)ninst;
+        blk += (q + T_THREADS - 1) / T_THREADS;
+    }
+    for (int t = L::ntasks; t <= T_MAXTASKS; ++t) g.blk0[t] = (unsigned)blk;
+    if (blk > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    dim3 grid((unsigned)blk, 1, 1), block(T_THREADS, 1, 1);
+    auto kfn = t_kernel<tz_t, SNFFT_TZ_KIND, SNFFT_TZ_INV != 0>;
+#if SNFFT_TZ_INV
+    SNFFT_LAUNCH(kfn, grid, block, 0, st, (tz_t*)z, (tz_t*)x, (const tz_t*)xk, (unsigned)ninst, g);
+#else
+    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const tz_t*)z, (const tz_t*)x, (tz_t*)xk, (unsigned)ninst, g);
+#endif
+    return (int)cudaGetLastError();
+}
+
+#endif
