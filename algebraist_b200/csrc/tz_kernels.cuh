@@ -96,7 +96,47 @@ z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, const ZGrou
 #endif
 
 // ---- T kernel --------------------------------------------------------------------------------------------
-// A task is (mu of k-1, alpha of 7); a thread is (row r of alpha, column c of mu, instance).
+// A task is (mu of k-1, alpha of 7); a thread is (row r of alpha, column c of mu, NV adjacent instances).
+// The generated code is elementwise in the instance, so it runs unchanged on a short vector of instances:
+// 16-byte (8-byte) global transfers, NV times the bytes in flight per thread and 1/NV of the index arithmetic
+// (with scalar threads the kernel is latency bound: <= 10 loads of 4 bytes per thread at level 9).
+template <typename S, int NV>
+struct alignas(sizeof(S) * NV) TzVec {
+    S v[NV];
+    TzVec() = default;
+    __host__ __device__ __forceinline__ explicit TzVec(double x) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = (S)x;
+    }
+};
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> operator*(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
+    TzVec<S, NV> r;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] * b.v[i];
+    return r;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> operator+(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
+    TzVec<S, NV> r;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] + b.v[i];
+    return r;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> operator-(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
+    TzVec<S, NV> r;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] - b.v[i];
+    return r;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> operator-(const TzVec<S, NV>& a) {
+    TzVec<S, NV> r;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r.v[i] = -a.v[i];
+    return r;
+}
 struct TTasks {
     int ntasks;
     unsigned blk0[T_MAXTASKS + 1];
@@ -104,6 +144,7 @@ struct TTasks {
 };
 
 #if SNFFT_TZ_KIND != 0
+// T = S (scalar threads) or TzVec<S, NV>; s = NINST_k / NV
 template <typename T, int K, bool INV>
 __global__ void __launch_bounds__(T_THREADS, 2)
 t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::conditional<INV, T*, const T*>::type xb,

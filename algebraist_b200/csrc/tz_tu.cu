@@ -15,6 +15,7 @@
 #define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -34,6 +35,9 @@ typedef float tz_t;
 #define TZ_DIR inv
 #else
 #define TZ_DIR fwd
+#endif
+#ifndef TZ_VEC_DEFAULT
+#define TZ_VEC_DEFAULT 4
 #endif
 #define TZ_CAT3_(a, b, c) a##b##_##c
 #define TZ_CAT3(a, b, c) TZ_CAT3_(a, b, c)
@@ -162,6 +166,15 @@ extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_
     using L = TzLevel<SNFFT_TZ_KIND>;
     static_assert(L::ntasks <= T_MAXTASKS, "too many T tasks");
     if (ninst <= 0 || ninst >= (1ll << 32)) return (int)cudaErrorInvalidValue;
+    // instances per thread: 16-byte transfers when the instance count and the buffers allow it (SNFFT_TZ_VEC=1|2|4 caps it)
+    static const int vec_cap = [] {
+        const char* e = std::getenv("SNFFT_TZ_VEC");
+        return e ? std::atoi(e) : TZ_VEC_DEFAULT;
+    }();
+    int nv = 16 / (int)sizeof(tz_t);
+    if (nv > vec_cap) nv = vec_cap < 1 ? 1 : vec_cap;
+    while (nv > 1 && (ninst % nv != 0 || ((uintptr_t)z | (uintptr_t)x | (uintptr_t)xk) % (sizeof(tz_t) * nv) != 0)) nv >>= 1;
+    ninst /= nv;
     TTasks g;
     g.ntasks = L::ntasks;
     unsigned long long blk = 0;
@@ -175,12 +188,31 @@ extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_
     for (int t = L::ntasks; t <= T_MAXTASKS; ++t) g.blk0[t] = (unsigned)blk;
     if (blk > 0x7fffffffull) return (int)cudaErrorInvalidValue;
     dim3 grid((unsigned)blk, 1, 1), block(T_THREADS, 1, 1);
-    auto kfn = t_kernel<tz_t, SNFFT_TZ_KIND, SNFFT_TZ_INV != 0>;
 #if SNFFT_TZ_INV
-    SNFFT_LAUNCH(kfn, grid, block, 0, st, (tz_t*)z, (tz_t*)x, (const tz_t*)xk, (unsigned)ninst, g);
+#define TZ_T_LAUNCH(VT)                                                                                   \
+    {                                                                                                     \
+        auto kfn = t_kernel<VT, SNFFT_TZ_KIND, true>;                                                     \
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (VT*)z, (VT*)x, (const VT*)xk, (unsigned)ninst, g);         \
+    }
 #else
-    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const tz_t*)z, (const tz_t*)x, (tz_t*)xk, (unsigned)ninst, g);
+#define TZ_T_LAUNCH(VT)                                                                                   \
+    {                                                                                                     \
+        auto kfn = t_kernel<VT, SNFFT_TZ_KIND, false>;                                                    \
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const VT*)z, (const VT*)x, (VT*)xk, (unsigned)ninst, g);   \
+    }
 #endif
+    if (nv == 4) {
+#if !SNFFT_TZ_F64
+        using V4 = TzVec<tz_t, 4>;
+        TZ_T_LAUNCH(V4)
+#endif
+    } else if (nv == 2) {
+        using V2 = TzVec<tz_t, 2>;
+        TZ_T_LAUNCH(V2)
+    } else {
+        TZ_T_LAUNCH(tz_t)
+    }
+#undef TZ_T_LAUNCH
     return (int)cudaGetLastError();
 }
 
