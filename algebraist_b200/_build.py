@@ -27,12 +27,12 @@ def col_deps(k):
 
 
 def tz_deps(kind):
-    gen = "tz_gen_z7.cuh" if kind == 0 else f"tz_gen_t{kind}.cuh"
+    gen = f"tz_gen_z{kind}.cuh" if kind <= 8 else f"tz_gen_t{kind}.cuh"
     return [os.path.join(CSRC, f) for f in ("tz_tu.cu", "tz_kernels.cuh", "tz_gen_tab.cuh", gen)]
 
 
-# top / bottom kernels (csrc/tz_tu.cu): kind 0 = Z kernel, 9 / 10 = T kernel of that level
-TZ_COMBOS = [(kind, f64, inv) for kind in (0, 9, 10) for f64 in (0, 1) for inv in (0, 1)]
+# top / bottom kernels (csrc/tz_tu.cu): kind 7 / 8 = Z kernel with that bottom level, 9 / 10 / 11 = T kernel of that level
+TZ_COMBOS = [(kind, f64, inv) for kind in (8, 7, 11, 10, 9) for f64 in (0, 1) for inv in (0, 1)]
 COL_COMBOS = [(k, f64, inv) for k in (6, 7, 8) for f64 in (0, 1) for inv in (0, 1)]
 COL9_PARTS = 4        # level 9, forward only: gen_col.SPLIT_FWD
 # threads per CTA of the column kernels by (level, fp64); default 128.  One large CTA per SM keeps all its warps on
@@ -68,7 +68,7 @@ def generate_col_headers(force: bool = False):
             ("gen_col.py", ("gen_col.py", "gen_base.py"),
              [f"col_gen_{k}.cuh" for k in (6, 7, 8)] + [f"col_gen_9p{p}.cuh" for p in range(COL9_PARTS)]),
             ("gen_tz.py", ("gen_tz.py", "gen_col.py", "gen_base.py"),
-             ["tz_gen_z7.cuh", "tz_gen_tab.cuh", "tz_gen_t9.cuh", "tz_gen_t10.cuh"])):
+             ["tz_gen_z7.cuh", "tz_gen_z8.cuh", "tz_gen_tab.cuh", "tz_gen_t9.cuh", "tz_gen_t10.cuh", "tz_gen_t11.cuh"])):
         gens = [os.path.join(CSRC, f) for f in gen_names]
         heads = [os.path.join(CSRC, f) for f in head_names]
         # the generators only rewrite a header whose contents change, so an edit of a generator that leaves the

@@ -44,6 +44,9 @@ SIGNATURES = {
     "snfft_forward": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "snfft_inverse": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "snfft_forward_cosets_workspace_bytes": (ctypes.c_size_t, [c_vp, c_vp, c_i64, c_int]),
+    "snfft_forward_cosets2_workspace_bytes": (ctypes.c_size_t, [c_vp, c_vp, c_i64, c_int]),
+    "snfft_forward_cosets2": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_vp, c_vp,
+                                      ctypes.c_size_t, c_vp]),
     "snfft_forward_cosets": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_int), c_int, c_vp, c_vp, ctypes.c_size_t,
                                      c_vp]),
     "snfft_power": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
@@ -55,6 +58,8 @@ SIGNATURES = {
     "snfft_coset_index": (c_int, [c_int, c_int, c_vp, c_vp]),
     "snfft_chain_index": (c_int, [c_int, c_vp, c_vp]),
     "snfft_dense_rep": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "snfft_rho": (c_int, [c_vp, c_int, ctypes.POINTER(c_int), c_vp, c_vp]),
+    "snfft_translate": (c_int, [c_int, c_int, c_vp, c_i64, ctypes.POINTER(c_int), c_int, c_vp, c_vp]),
     "snfft_profile_begin": (c_int, [c_vp]),
     "snfft_profile_end": (c_int, [c_vp, ctypes.POINTER(ProfileRecord), c_int, ctypes.POINTER(c_int)]),
     "snfft_launch_count": (c_i64, []),

@@ -36,10 +36,10 @@ import math
 import os
 
 from gen_base import ScaledEmitter, boffs, children, coef_off, dim, partitions
-from gen_col import forward_task, inverse_task, need_chain, sweep_need, value_expr, write_if_changed
+from gen_col import forward_task, inverse_task, need_chain, row_sets, sweep_need, value_expr, write_if_changed
 
-MB = 7
-LEVELS = (9, 10)
+LEVEL_MB = {9: 7, 10: 7, 11: 8}        # level k -> bottom level MB (the Z kernel runs level-MB column operators)
+LEVELS = tuple(LEVEL_MB)
 
 
 def parents(part):
@@ -60,6 +60,10 @@ def subblocks(part, depth):
 
 def aoff(zeta, alpha):
     """Row offset of the parent alpha inside the MB d_zeta rows of a piece (parents in partition order)."""
+    return _aoff(zeta, alpha)
+
+
+def _aoff(zeta, alpha):
     off = 0
     for a in parents(zeta):
         if a == alpha:
@@ -71,7 +75,9 @@ def aoff(zeta, alpha):
 # ----------------------------------------------------------------------------
 # Z kernel code: level-MB column operators with run-time strides
 # ----------------------------------------------------------------------------
-def gen_z(inverse):
+def gen_z(MB, inverse):
+    """Level-MB column operators.  Forward: one task per (zeta, parent alpha, row set of alpha): all rows for
+    MB = 7, one child block of alpha for MB = 8 (as in gen_col.py).  Inverse: one task per (zeta, coset i)."""
     tag = f"zb{MB}{'i' if inverse else 'f'}"
     funcs, cases, groups = [], [], []
     task = 0
@@ -81,6 +87,7 @@ def gen_z(inverse):
         task0 = task
         if not inverse:
             for alpha in parents(zeta):
+              for rows in row_sets(MB, alpha):
                 em = ScaledEmitter()
                 cache = {}
 
@@ -92,12 +99,12 @@ def gen_z(inverse):
                 def store(t, v, em=em, ao=aoff(zeta, alpha)):
                     em.lines.append(f"    out[(size_t){ao + t} * zs] = {value_expr(v)};")
 
-                forward_task(em, MB, alpha, children(alpha).index(zeta), list(range(dim(alpha))), load, store)
+                forward_task(em, MB, alpha, children(alpha).index(zeta), rows, load, store)
                 total += em.n
                 funcs.append("\n".join([
                     "template <typename T>",
                     f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned rs, unsigned s, unsigned zs) {{"
-                    f"   // {alpha} <- {zeta}"] + em.lines + ["}"]) + "\n")
+                    f"   // {alpha} <- {zeta}, rows {rows[0]}..{rows[-1]}"] + em.lines + ["}"]) + "\n")
                 cases.append(f"        case {task}: {tag}_{task}<T>(in, out, rs, s, zs); break;")
                 task += 1
         else:
@@ -122,7 +129,7 @@ def gen_z(inverse):
     inv = "true" if inverse else "false"
     code = funcs
     code.append("\n".join([
-        f"template <> struct ZInfo<{inv}> {{",
+        f"template <> struct ZInfo<{MB}, {inv}> {{",
         f"    static constexpr int ngroups = {len(groups)};",
         f"    static constexpr int ntasks = {task};",
         "    static const int* task0() { static const int v[] = {" + ", ".join(str(g[1]) for g in groups) + "}; return v; }",
@@ -139,6 +146,7 @@ def gen_z(inverse):
 # T kernel code: the top sweeps of level k, one function per (mu, alpha)
 # ----------------------------------------------------------------------------
 def t_tasks(k):
+    MB = LEVEL_MB[k]
     s = k - MB
     out = []
     for mu in partitions(k - 1):
@@ -154,6 +162,7 @@ def t_tasks(k):
 
 
 def t_forward(em, k, mu, alpha):
+    MB = LEVEL_MB[k]
     s = k - MB
     dmu, da = dim(mu), dim(alpha)
     zcache, xcache = {}, {}
@@ -213,6 +222,7 @@ def t_forward(em, k, mu, alpha):
 
 
 def t_inverse(em, k, mu, alpha):
+    MB = LEVEL_MB[k]
     s = k - MB
     dmu, da = dim(mu), dim(alpha)
     pieces = [(P, off) for P, off in subblocks(mu, s) if P[-1] in children(alpha)]
@@ -289,7 +299,6 @@ def gen_t(k, inverse):
             head.append(f"    {cl}T* __restrict__ {'ib' if inverse else 'ob'}{li} = lb + (size_t)(r * {dl}u + c) * s;")
         funcs.append("\n".join(head + em.lines + ["}"]) + "\n")
         cases.append(f"        case {task}: {tag}_{task}<T>(zb, xb, lb, r, c, s); break;")
-    inv = "true" if inverse else "false"
     code = funcs
     code.append("\n".join([
         "template <typename T>",
@@ -301,6 +310,7 @@ def gen_t(k, inverse):
 
 def level_tables(k):
     """Static tables of level k: T tasks (d_alpha, d_mu) and the segments of the Z kernel by group (zeta)."""
+    MB = LEVEL_MB[k]
     s = k - MB
     tasks = t_tasks(k)
     zetas = list(partitions(MB - 1))
@@ -313,6 +323,7 @@ def level_tables(k):
                     segs.append((g, (coef_off(mu) + off * dmu) * k, MB * (coef_off(mu) + off * dmu), dmu))
     lines = [
         f"template <> struct TzLevel<{k}> {{",
+        f"    static constexpr int MB = {MB};",
         f"    static constexpr int ntasks = {len(tasks)};",
         f"    static constexpr int nsegs = {len(segs)};",
         "    static const int* t_dal() { static const int v[] = {" + ", ".join(str(dim(a)) for _, a in tasks) + "}; return v; }",
@@ -337,13 +348,14 @@ TAIL = ["}  // namespace", "}  // namespace snfft"]
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
     stats = {}
-    parts = [f"// GENERATED by gen_tz.py -- do not edit.  Level-{MB} column operators with run-time strides (Z kernel)."] + HEAD
-    parts.append("template <bool INV> struct ZInfo;\n")
-    for inverse in (False, True):
-        code, ntask, n = gen_z(inverse)
-        stats[("z", inverse)] = (ntask, n)
-        parts.append(code)
-    write_if_changed(os.path.join(here, f"tz_gen_z{MB}.cuh"), "\n".join(parts + TAIL) + "\n")
+    for MB in sorted(set(LEVEL_MB.values())):
+        parts = [f"// GENERATED by gen_tz.py -- do not edit.  Level-{MB} column operators with run-time strides (Z kernel)."] + HEAD
+        parts.append("template <int MB, bool INV> struct ZInfo;\n")
+        for inverse in (False, True):
+            code, ntask, n = gen_z(MB, inverse)
+            stats[(f"z{MB}", inverse)] = (ntask, n)
+            parts.append(code)
+        write_if_changed(os.path.join(here, f"tz_gen_z{MB}.cuh"), "\n".join(parts + TAIL) + "\n")
     for k in LEVELS:
         parts = [f"// GENERATED by gen_tz.py -- do not edit.  Top sweeps of the level step k = {k} (T kernel) and the tables of",
                  "// its Z kernel launches."] + HEAD
@@ -351,6 +363,21 @@ def main():
             code, n = gen_t(k, inverse)
             stats[(k, inverse)] = (len(t_tasks(k)), n)
             parts.append(code)
+        tasks = t_tasks(k)
+        parts.append("\n".join([
+            "// per task: d_alpha, d_mu (device copies of TzLevel<K>::t_dal / t_dmu)",
+            f"static __device__ const unsigned short tz{k}_dal[] = {{" + ", ".join(str(dim(a)) for _, a in tasks) + "};",
+            f"static __device__ const unsigned short tz{k}_dmu[] = {{" + ", ".join(str(dim(m)) for m, _ in tasks) + "};",
+            "template <int K> struct TzDev;",
+            f"template <> struct TzDev<{k}> {{",
+            f"    static __device__ __forceinline__ unsigned dal(int t) {{ return tz{k}_dal[t]; }}",
+            f"    static __device__ __forceinline__ unsigned dmu(int t) {{ return tz{k}_dmu[t]; }}",
+            "    template <typename T, bool INV, typename PZ, typename PL>",
+            "    static __device__ __forceinline__ void run(int task, PZ zb, PZ xb, PL lb, unsigned r, unsigned c, unsigned s) {",
+            f"        if constexpr (!INV) tz{k}f_run<T>(task, zb, xb, lb, r, c, s);",
+            f"        else tz{k}i_run<T>(task, zb, xb, lb, r, c, s);",
+            "    }",
+            "};"]) + "\n")
         write_if_changed(os.path.join(here, f"tz_gen_t{k}.cuh"), "\n".join(parts + TAIL) + "\n")
     parts = ["// GENERATED by gen_tz.py -- do not edit.  Task and segment tables of the T / Z kernels per level."] + HEAD
     parts.append("template <int K> struct TzLevel;\n")

@@ -1077,6 +1077,84 @@ __global__ void restrict_kernel(const T* __restrict__ f, T* __restrict__ out, co
     out[e] = f[b * ra.ia.nfact + src];
 }
 
+// Two nested restrictions (coset i_n of S_n, then coset i_{n-1} of S_{n-1}) for a list of pairs:
+//   out[(p * B + b) * (n-2)! + r''] = f[b * n! + idx^n_{i_n[p]}( idx^{n-1}_{i_{n-1}[p]}(r'') )]
+// The pairs of ONE function are the unit of work of the coset-sharded transform (n (n-1) two-level cosets).
+constexpr int RESTRICT2_MAXPAIRS = SNFFT_MAX_N * (SNFFT_MAX_N - 1);
+struct Restrict2Args {
+    IndexArgs ia;
+    long long batch;
+    int npairs;
+    unsigned char top[RESTRICT2_MAXPAIRS], sub[RESTRICT2_MAXPAIRS];
+};
+
+// 32-bit arithmetic: n! < 2^32 for n <= 12 (SNFFT_MAX_N); the 64-bit divisions of coset_index_kernel cost
+// about ten times as much and this runs once per element of the function
+__device__ __forceinline__ unsigned coset_lift(int n, int coset, unsigned r, const long long* fact) {
+    unsigned out = (unsigned)(n - 1 - coset) * (unsigned)fact[n - 1 - coset];
+    unsigned rem = r;
+    for (int j = 0; j < n - 1; ++j) {
+        const unsigned fj = (unsigned)fact[n - 2 - j];
+        const unsigned lj = rem / fj;
+        rem -= lj * fj;
+        const int pos = j < coset ? j : j + 1;
+        out += lj * (unsigned)fact[n - 1 - pos];
+    }
+    return out;
+}
+
+template <typename T>
+__global__ void restrict2_kernel(const T* __restrict__ f, T* __restrict__ out, const Restrict2Args ra) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = ra.ia.n;
+    const long long fm = ra.ia.fact[n - 2];
+    if (e >= (long long)ra.npairs * ra.batch * fm) return;
+    const long long pb = e / fm;
+    const unsigned r = (unsigned)(e - pb * fm);
+    const long long b = pb % ra.batch;
+    const int p = (int)(pb / ra.batch);
+    const unsigned mid = coset_lift(n - 1, ra.sub[p], r, ra.ia.fact);
+    out[e] = f[b * ra.ia.nfact + coset_lift(n, ra.top[p], mid, ra.ia.fact)];
+}
+
+// Level array of the pairs' sub-transforms -> level array n-2 of the full transform, zero where a pair is absent:
+//   dst[e * ninst_full + slot[p] + b] = src[e * (npairs * B) + p * B + b],   slot[p] = (i_{n-1} n + i_n) B
+// (instance of level n-2 = i_{n-1} NINST_{n-1} + i_n B + b).  dst is zeroed beforehand.
+struct ExpandArgs {
+    long long batch, ncoef, ninst_full;
+    int npairs;
+    int slot[RESTRICT2_MAXPAIRS];
+};
+
+template <typename T>
+__global__ void expand_pairs_kernel(const T* __restrict__ src, T* __restrict__ dst, const ExpandArgs ea) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ni = (long long)ea.npairs * ea.batch;
+    if (q >= ea.ncoef * ni) return;
+    const long long e = q / ni, pb = q - e * ni;
+    const int p = (int)(pb / ea.batch);
+    const long long b = pb - (long long)p * ea.batch;
+    dst[e * ea.ninst_full + ea.slot[p] + b] = src[q];
+}
+
+// Input permutation / output scatter for SMALL batches (restrict_to_coset composed over all levels,
+// fourier.py:63-80,253; inverse lift_from_coset, fourier.py:46-60): a thread owns one rank r and walks over the
+// batch, x1[p1(r) * B + b] <-> f[b * n! + r].  The function side is coalesced across threads, the level side moves
+// B consecutive elements per rank.  One function (B = 1, the coset-sharded transform of a large function) runs
+// at the speed of a permutation with 4-byte granularity instead of the tile transposes sized for large batches.
+template <typename T, bool SCATTER>
+__global__ void __launch_bounds__(256) gather_small_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                           const uint32_t* __restrict__ p1tab, const IndexArgs ia) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ia.nfact) return;
+    const long long p1 = p1tab ? (long long)p1tab[r] : chain_index(ia.n, r, ia.fact);
+    const long long B = ia.batch;
+    for (long long b = 0; b < B; ++b) {
+        if (!SCATTER) out[p1 * B + b] = in[b * ia.nfact + r];
+        else out[b * ia.nfact + r] = in[p1 * B + b];
+    }
+}
+
 __global__ void chain_index32_kernel(uint32_t* __restrict__ p1, const IndexArgs ia) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= ia.nfact) return;
@@ -1132,6 +1210,64 @@ __global__ void __launch_bounds__(32) dense_rep_kernel(const RowTables<T> tb, in
     for (int t = 0; t < d; ++t) out[(rank * d + t) * d + c] = x[t * 32 + lane];
 }
 
+
+// rho_lambda(sigma) for ONE permutation (SnIrrep.matrix_representations[sigma], irreps.py:122-141): the same word
+// of adjacent transpositions as dense_rep_kernel, applied to the unit vector e_c by CTA c with the column in
+// shared memory (any d: 2310 rows at n = 11 are 18 KB in fp64).   grid (d), 128 threads, 2 d elements of shared memory
+struct PermArg {
+    int sig[SNFFT_MAX_N];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) rho_kernel(const RowTables<T> tb, int d, int n, const PermArg pa, T* __restrict__ out) {
+    SNFFT_DYN_SMEM(smem_raw);
+    T* x = reinterpret_cast<T*>(smem_raw);
+    T* y = x + d;
+    const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    for (int t = tid; t < d; t += nt) x[t] = (t == c) ? T(1) : T(0);
+    __syncthreads();
+    for (int k = 2; k <= n; ++k) {
+        const int v = k - 1;
+        int i = 0;
+        for (int p = 0; p < n; ++p) {
+            if (pa.sig[p] == v) break;
+            i += pa.sig[p] < v;
+        }
+        for (int j = k - 2; j >= i; --j) {
+            const int* __restrict__ pt = tb.partner + (size_t)j * d;
+            const T* __restrict__ dg = tb.diag + (size_t)j * d;
+            const T* __restrict__ of = tb.off + (size_t)j * d;
+            for (int t = tid; t < d; t += nt) y[t] = dg[t] * x[t] + of[t] * x[pt[t]];
+            __syncthreads();
+            T* tmp = x;
+            x = y;
+            y = tmp;
+        }
+    }
+    for (int t = tid; t < d; t += nt) out[(size_t)t * d + c] = x[t];
+}
+
+// Translation of functions on S_n by a fixed permutation (reference tests/test_fourier.py:112-121):
+//   left : out[b][k] = f[b][rank(pi^-1 * p_k)],   (a * b)[i] = b[a[i]]  (permutations.py:85-88)
+//   right: out[b][k] = f[b][rank(p_k * pi^-1)]
+// A thread owns one rank k (unrank, compose, rank: bit exact integer work) and walks over the batch.
+struct TranslateArgs {
+    IndexArgs ia;
+    int pinv[SNFFT_MAX_N];
+    int right;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) translate_kernel(const T* __restrict__ f, T* __restrict__ out, const TranslateArgs ta) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = ta.ia.n;
+    if (k >= ta.ia.nfact) return;
+    int p[SNFFT_MAX_N], q[SNFFT_MAX_N];
+    unrank_perm(n, k, ta.ia.fact, p);
+    for (int i = 0; i < n; ++i) q[i] = ta.right ? ta.pinv[p[i]] : p[ta.pinv[i]];
+    const long long src = rank_perm(n, q, ta.ia.fact);
+    for (long long b = 0; b < ta.ia.batch; ++b) out[b * ta.ia.nfact + k] = f[b * ta.ia.nfact + src];
+}
 
 // ---------------------------------------------------------------------------
 // Per-partition products of two packed coefficient arrays: C_lambda[b] = A_lambda[b] . B_lambda[b]

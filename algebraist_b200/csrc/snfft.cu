@@ -32,6 +32,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -531,6 +532,15 @@ static int run_gather(const snfft_plan* p, const void* in, void* out, long long 
         SNFFT_CUDA(cudaGetLastError());
         return SNFFT_OK;
     }
+    if (B <= 8 && g_no_vec_gather.load() == 0) {         // small batches: one thread per rank (kernel_class -6)
+        dim3 grid((unsigned)((ia.nfact + 255) / 256), 1, 1), block(256, 1, 1);
+        ProfScope prof(p, st, SCATTER ? 3 : 2, 1, -6, ia.nfact);
+        auto kfn = gather_small_kernel<T, SCATTER>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)in, (T*)out, (const uint32_t*)p->d_p1, ia);
+        g_launches.fetch_add(1);
+        SNFFT_CUDA(cudaGetLastError());
+        return SNFFT_OK;
+    }
     dim3 grid((unsigned)((ia.nfact + GS_TR - 1) / GS_TR), (unsigned)((B + GS_TB - 1) / GS_TB), 1);
     dim3 block(GS_THREADS, 1, 1);
     ProfScope prof(p, st, SCATTER ? 3 : 2, 1, -1, ia.nfact);
@@ -589,6 +599,11 @@ template <typename T, bool TO_PACKED>
 static int run_pack(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
     const HostLevel& L = p->host.levels[p->n];
     constexpr int VT = 16 / (int)sizeof(T);
+    if (B == 1) {        // one function: [d][d][1] per partition IS the packed layout, a plain copy
+        ProfScope prof(p, st, TO_PACKED ? 6 : 7, p->n, -6, p->host.factorial[p->n]);
+        SNFFT_CUDA(cudaMemcpyAsync(out, in, (size_t)p->host.factorial[p->n] * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        return SNFFT_OK;
+    }
     if (B % VT == 0 && (uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0 && g_no_vec_gather.load() == 0) {
         const void* prefix = sizeof(T) == 4 ? p->d_vtile_prefix32 : p->d_vtile_prefix64;
         const long long vt = sizeof(T) == 4 ? p->n_vtiles32 : p->n_vtiles64;
@@ -693,14 +708,18 @@ static int run_col_level(const snfft_plan* p, int k, const void* in, void* out, 
 // Top / bottom kernels (tz_kernels.cuh / tz_tu.cu: one translation unit per kernel, dtype and direction).
 extern "C" {
 #define SNFFT_TZ_DECL(dt, dir)                                                                 \
-    int snfft_tz_z_##dt##_##dir(int, const void*, void*, long long, cudaStream_t);             \
-    int snfft_tz_z_prepare_##dt##_##dir(int);                                                  \
+    int snfft_tz_z7_##dt##_##dir(int, const void*, void*, long long, cudaStream_t);            \
+    int snfft_tz_z8_##dt##_##dir(int, const void*, void*, long long, cudaStream_t);            \
+    int snfft_tz_z7_prepare_##dt##_##dir(int);                                                 \
+    int snfft_tz_z8_prepare_##dt##_##dir(int);                                                 \
     int snfft_tz_t9_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);                \
-    int snfft_tz_t10_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);
+    int snfft_tz_t10_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);               \
+    int snfft_tz_t11_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);
 SNFFT_TZ_DECL(f32, fwd) SNFFT_TZ_DECL(f32, inv) SNFFT_TZ_DECL(f64, fwd) SNFFT_TZ_DECL(f64, inv)
 #undef SNFFT_TZ_DECL
 }
-constexpr int kTzFirst = 9, kTzLast = 10, kTzMB = 7;
+constexpr int kTzFirst = 9, kTzLast = 11;
+static int tz_mb(int k) { return k == 11 ? 8 : 7; }       // gen_tz.py LEVEL_MB
 
 // Levels that use the top / bottom kernels: automatic kernel choice only; SNFFT_TZ_FWD / SNFFT_TZ_INV (lists of
 // levels, "" = none) override when a plan is created.  They take precedence over the column kernels.
@@ -713,8 +732,14 @@ static void tz_pick_dirs(int k, bool* fwd, bool* inv) {
 
 static int tz_prepare(int dtype, int k, bool fwd, bool inv) {
     int rc = 0;
-    if (fwd) rc = dtype == SNFFT_F32 ? snfft_tz_z_prepare_f32_fwd(k) : snfft_tz_z_prepare_f64_fwd(k);
-    if (!rc && inv) rc = dtype == SNFFT_F32 ? snfft_tz_z_prepare_f32_inv(k) : snfft_tz_z_prepare_f64_inv(k);
+    const bool f32 = dtype == SNFFT_F32;
+    if (tz_mb(k) == 7) {
+        if (fwd) rc = f32 ? snfft_tz_z7_prepare_f32_fwd(k) : snfft_tz_z7_prepare_f64_fwd(k);
+        if (!rc && inv) rc = f32 ? snfft_tz_z7_prepare_f32_inv(k) : snfft_tz_z7_prepare_f64_inv(k);
+    } else {
+        if (fwd) rc = f32 ? snfft_tz_z8_prepare_f32_fwd(k) : snfft_tz_z8_prepare_f64_fwd(k);
+        if (!rc && inv) rc = f32 ? snfft_tz_z8_prepare_f32_inv(k) : snfft_tz_z8_prepare_f64_inv(k);
+    }
     if (rc) return set_error(SNFFT_ECUDA, std::string("top/bottom kernel tables: ") + cudaGetErrorString((cudaError_t)rc));
     return SNFFT_OK;
 }
@@ -729,28 +754,37 @@ static int run_tz_level(const snfft_plan* p, int k, const void* in, void* out, v
     int rc;
     auto fail = [](int e) { return set_error(SNFFT_ECUDA, std::string("top/bottom kernel launch: ") + cudaGetErrorString((cudaError_t)e)); };
     constexpr bool F32 = sizeof(T) == 4;
+    const int mb = tz_mb(k);
+    typedef int (*zfn_t)(int, const void*, void*, long long, cudaStream_t);
+    typedef int (*tfn_t)(void*, void*, void*, long long, cudaStream_t);
+    zfn_t zfn;
+    tfn_t tfn;
     if (!INVERSE) {
+        zfn = mb == 7 ? (F32 ? snfft_tz_z7_f32_fwd : snfft_tz_z7_f64_fwd) : (F32 ? snfft_tz_z8_f32_fwd : snfft_tz_z8_f64_fwd);
+        tfn = k == 9 ? (F32 ? snfft_tz_t9_f32_fwd : snfft_tz_t9_f64_fwd)
+                     : (k == 10 ? (F32 ? snfft_tz_t10_f32_fwd : snfft_tz_t10_f64_fwd) : (F32 ? snfft_tz_t11_f32_fwd : snfft_tz_t11_f64_fwd));
         {
-            ProfScope prof(p, st, 0, k, -4, fk * kTzMB / k);
-            rc = F32 ? snfft_tz_z_f32_fwd(k, in, z, ninst, st) : snfft_tz_z_f64_fwd(k, in, z, ninst, st);
+            ProfScope prof(p, st, 0, k, -4, fk * mb / k);
+            rc = zfn(k, in, z, ninst, st);
             g_launches.fetch_add(1);
             if (rc) return fail(rc);
         }
         ProfScope prof(p, st, 0, k, -5, fk);
-        if (k == 9) rc = F32 ? snfft_tz_t9_f32_fwd(z, (void*)in, out, ninst, st) : snfft_tz_t9_f64_fwd(z, (void*)in, out, ninst, st);
-        else rc = F32 ? snfft_tz_t10_f32_fwd(z, (void*)in, out, ninst, st) : snfft_tz_t10_f64_fwd(z, (void*)in, out, ninst, st);
+        rc = tfn(z, (void*)in, out, ninst, st);
         g_launches.fetch_add(1);
         if (rc) return fail(rc);
     } else {
+        zfn = mb == 7 ? (F32 ? snfft_tz_z7_f32_inv : snfft_tz_z7_f64_inv) : (F32 ? snfft_tz_z8_f32_inv : snfft_tz_z8_f64_inv);
+        tfn = k == 9 ? (F32 ? snfft_tz_t9_f32_inv : snfft_tz_t9_f64_inv)
+                     : (k == 10 ? (F32 ? snfft_tz_t10_f32_inv : snfft_tz_t10_f64_inv) : (F32 ? snfft_tz_t11_f32_inv : snfft_tz_t11_f64_inv));
         {
             ProfScope prof(p, st, 1, k, -5, fk);
-            if (k == 9) rc = F32 ? snfft_tz_t9_f32_inv(z, out, (void*)in, ninst, st) : snfft_tz_t9_f64_inv(z, out, (void*)in, ninst, st);
-            else rc = F32 ? snfft_tz_t10_f32_inv(z, out, (void*)in, ninst, st) : snfft_tz_t10_f64_inv(z, out, (void*)in, ninst, st);
+            rc = tfn(z, out, (void*)in, ninst, st);
             g_launches.fetch_add(1);
             if (rc) return fail(rc);
         }
-        ProfScope prof(p, st, 1, k, -4, fk * kTzMB / k);
-        rc = F32 ? snfft_tz_z_f32_inv(k, z, out, ninst, st) : snfft_tz_z_f64_inv(k, z, out, ninst, st);
+        ProfScope prof(p, st, 1, k, -4, fk * mb / k);
+        rc = zfn(k, z, out, ninst, st);
         g_launches.fetch_add(1);
         if (rc) return fail(rc);
     }
@@ -758,6 +792,22 @@ static int run_tz_level(const snfft_plan* p, int k, const void* in, void* out, v
 }
 
 static IndexArgs make_index_args(int n);
+
+// level steps k_first .. n of the forward pipeline: cur = X_{k_first - 1} on entry, X_n on return
+template <typename T>
+static int forward_level_range(const snfft_plan* p, int k_first, void*& cur, void*& nxt, void* zbuf, long long B, cudaStream_t st) {
+    const int base = g_no_base.load();
+    for (int k = k_first; k <= p->n; ++k) {
+        int rc;
+        if (base == 0 && p->lev[k].tz_fwd) rc = run_tz_level<T, false>(p, k, cur, nxt, zbuf, B, st);
+        else if (base == 0 && p->lev[k].col_fwd) rc = run_col_level<T, false>(p, k, cur, nxt, B, st);
+        else if (p->lev[k].tb_s > 0 && p->lev[k].tb_fwd) rc = run_tb_level<T, false>(p, k, cur, nxt, B, st);
+        else rc = run_fwd_level<T>(p, k, cur, nxt, B, st);
+        if (rc) return rc;
+        std::swap(cur, nxt);
+    }
+    return SNFFT_OK;
+}
 
 // levels 1..n of the forward pipeline; *result points at X_n (instance fastest) inside the workspace
 template <typename T>
@@ -784,14 +834,7 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
         std::swap(cur, nxt);
         k_first = kBaseK0 + 1;
     }
-    for (int k = k_first; k <= p->n; ++k) {
-        if (base == 0 && p->lev[k].tz_fwd) rc = run_tz_level<T, false>(p, k, cur, nxt, zbuf, B, st);
-        else if (base == 0 && p->lev[k].col_fwd) rc = run_col_level<T, false>(p, k, cur, nxt, B, st);
-        else if (p->lev[k].tb_s > 0 && p->lev[k].tb_fwd) rc = run_tb_level<T, false>(p, k, cur, nxt, B, st);
-        else rc = run_fwd_level<T>(p, k, cur, nxt, B, st);
-        if (rc) return rc;
-        std::swap(cur, nxt);
-    }
+    if ((rc = forward_level_range<T>(p, k_first, cur, nxt, zbuf, B, st))) return rc;
     *result = cur;
     return SNFFT_OK;
 }
@@ -837,6 +880,62 @@ static int forward_cosets_impl(const snfft_plan* pn, const snfft_plan* pm, const
     if ((rc = run_fwd_level<T>(pn, n, xm, xn, B, st, ncos, cosets))) return rc;
     (void)fn;
     return run_pack<T, true>(pn, xn, F, B, st);
+}
+
+// The same partial transform over a subset of the n (n-1) TWO-level cosets {sigma : sigma[i] = n-1, then the
+// restriction's [j] = n-2} (finer units for 8 ranks than the n top-level cosets).  The pairs'
+// restrictions go through the S_{n-2} plan as one batch; their level arrays are placed at their instance slots
+// of a zeroed level-(n-2) array of the full transform, and the last two level steps run at full size: the terms
+// of absent pairs are zero, so the result is the partial sum (fourier.py:253-273 applied twice, by linearity).
+// workspace: [restricted input][S_{n-2} pipeline scratch][three level arrays of the full transform]
+template <typename T>
+static int forward_cosets2_impl(const snfft_plan* pn, const snfft_plan* pm, const void* f, long long B, const int* top,
+                                const int* sub, int npairs, void* F, void* ws, cudaStream_t st) {
+    const int n = pn->n;
+    const long long fm = pn->host.factorial[n - 2], fn = pn->host.factorial[n];
+    const long long Bm = (long long)npairs * B;
+    T* rin = (T*)ws;
+    void* wsm = (char*)ws + (size_t)Bm * fm * sizeof(T);
+    const size_t full = (size_t)B * fn * sizeof(T);
+    void* cur = (char*)wsm + snfft_workspace_bytes(pm, Bm);
+    void* nxt = (char*)cur + full;
+    void* zbuf = (char*)nxt + full;
+    {
+        Restrict2Args ra;
+        ra.ia = make_index_args(n);
+        ra.batch = B;
+        ra.npairs = npairs;
+        for (int j = 0; j < npairs; ++j) {
+            ra.top[j] = (unsigned char)top[j];
+            ra.sub[j] = (unsigned char)sub[j];
+        }
+        const long long total = Bm * fm;
+        dim3 grid((unsigned)((total + 255) / 256), 1, 1), block(256, 1, 1);
+        auto kfn = restrict2_kernel<T>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)f, rin, ra);
+        g_launches.fetch_add(1);
+        SNFFT_CUDA(cudaGetLastError());
+    }
+    void* xm = nullptr;
+    int rc = forward_levels<T>(pm, rin, Bm, wsm, st, &xm);
+    if (rc) return rc;
+    SNFFT_CUDA(cudaMemsetAsync(cur, 0, full, st));
+    {
+        ExpandArgs ea;
+        ea.batch = B;
+        ea.ncoef = fm;
+        ea.ninst_full = B * (long long)n * (n - 1);
+        ea.npairs = npairs;
+        for (int j = 0; j < npairs; ++j) ea.slot[j] = (int)(((long long)sub[j] * n + top[j]) * B);
+        const long long total = fm * Bm;
+        dim3 grid((unsigned)((total + 255) / 256), 1, 1), block(256, 1, 1);
+        auto kfn = expand_pairs_kernel<T>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)xm, (T*)cur, ea);
+        g_launches.fetch_add(1);
+        SNFFT_CUDA(cudaGetLastError());
+    }
+    if ((rc = forward_level_range<T>(pn, n - 1, cur, nxt, zbuf, B, st))) return rc;
+    return run_pack<T, true>(pn, cur, F, B, st);
 }
 
 template <typename T>
@@ -889,33 +988,76 @@ static IndexArgs make_index_args(int n) {
 
 }  // namespace snfft
 
+// Per-row YOR tables of level n ([n-1][d] per partition: partner, diagonal, off-diagonal in gather form), used by
+// snfft_dense_rep and snfft_rho.  Uploaded on first use under a lock; the pointers are published only after all
+// three uploads succeeded, so a failed or concurrent first call cannot leave a half-initialised plan behind.
+static std::mutex g_rt_mutex;
+
 template <typename T>
-static int dense_rep_impl(snfft_plan* p, int part, void* out, cudaStream_t st) {
+static int ensure_row_tables(snfft_plan* p) {
+    std::lock_guard<std::mutex> lock(g_rt_mutex);
+    if (p->rt_partner) return SNFFT_OK;
     const HostLevel& L = p->host.levels[p->n];
     const int n = p->n;
-    if (!p->rt_partner) {            // first use: upload the per-row tables of level n
-        std::vector<int32_t> pt;
-        std::vector<T> dg, of;
-        p->rt_base.clear();
-        for (const HostShape& S : L.shapes) {
-            p->rt_base.push_back((long long)pt.size());
-            for (int j = 0; j <= n - 2; ++j)
-                for (int t = 0; t < S.dim; ++t) {
-                    pt.push_back(S.partner[j][t]);
-                    dg.push_back((T)S.diag[j][t]);
-                    of.push_back(S.partner[j][t] == t ? (T)0 : (T)S.off[j][t]);
-                }
-        }
-        int rc;
-        if ((rc = upload(p, pt, &p->rt_partner))) return rc;
-        if ((rc = upload(p, dg, &p->rt_diag))) return rc;
-        if ((rc = upload(p, of, &p->rt_off))) return rc;
+    std::vector<int32_t> pt;
+    std::vector<T> dg, of;
+    std::vector<long long> base;
+    for (const HostShape& S : L.shapes) {
+        base.push_back((long long)pt.size());
+        for (int j = 0; j <= n - 2; ++j)
+            for (int t = 0; t < S.dim; ++t) {
+                pt.push_back(S.partner[j][t]);
+                dg.push_back((T)S.diag[j][t]);
+                of.push_back(S.partner[j][t] == t ? (T)0 : (T)S.off[j][t]);
+            }
     }
-    const int d = L.shapes[part].dim;
+    void *d_pt = nullptr, *d_dg = nullptr, *d_of = nullptr;
+    int rc;
+    if ((rc = upload(p, pt, &d_pt))) return rc;
+    if ((rc = upload(p, dg, &d_dg))) return rc;
+    if ((rc = upload(p, of, &d_of))) return rc;
+    p->rt_base = base;
+    p->rt_diag = d_dg;
+    p->rt_off = d_of;
+    p->rt_partner = d_pt;           // last: the readiness flag
+    return SNFFT_OK;
+}
+
+template <typename T>
+static RowTables<T> row_tables(const snfft_plan* p, int part) {
     RowTables<T> tb;
     tb.partner = (const int*)p->rt_partner + p->rt_base[part];
     tb.diag = (const T*)p->rt_diag + p->rt_base[part];
     tb.off = (const T*)p->rt_off + p->rt_base[part];
+    return tb;
+}
+
+template <typename T>
+static int rho_impl(snfft_plan* p, int part, const int* sigma, void* out, cudaStream_t st) {
+    int rc = ensure_row_tables<T>(p);
+    if (rc) return rc;
+    const int d = p->host.levels[p->n].shapes[part].dim;
+    PermArg pa;
+    for (int i = 0; i < SNFFT_MAX_N; ++i) pa.sig[i] = i < p->n ? sigma[i] : 0;
+    const size_t smem = (size_t)2 * d * sizeof(T);
+    dim3 grid((unsigned)d, 1, 1), block(128, 1, 1);
+    auto kfn = rho_kernel<T>;
+    if ((rc = set_smem(kfn, smem))) return rc;
+    SNFFT_LAUNCH(kfn, grid, block, smem, st, row_tables<T>(p, part), d, p->n, pa, (T*)out);
+    g_launches.fetch_add(1);
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
+}
+
+template <typename T>
+static int dense_rep_impl(snfft_plan* p, int part, void* out, cudaStream_t st) {
+    const HostLevel& L = p->host.levels[p->n];
+    {
+        const int rc0 = ensure_row_tables<T>(p);
+        if (rc0) return rc0;
+    }
+    const int d = L.shapes[part].dim;
+    const RowTables<T> tb = row_tables<T>(p, part);
     const long long q = p->ia.nfact * d;
     dim3 grid((unsigned)((q + 31) / 32), 1, 1), block(32, 1, 1);
     auto kfn = dense_rep_kernel<T>;
@@ -1149,6 +1291,44 @@ int snfft_forward_cosets(const snfft_plan_t* pn, const snfft_plan_t* pm, const v
                                   : forward_cosets_impl<double>(pn, pm, f, B, cosets, ncosets, F, ws, st);
 }
 
+size_t snfft_forward_cosets2_workspace_bytes(const snfft_plan_t* pn, const snfft_plan_t* pm, int64_t B, int npairs) {
+    if (!pn || !pm || B < 0 || npairs < 0) return 0;
+    const size_t Bm = (size_t)B * (size_t)npairs;
+    return Bm * (size_t)pm->host.factorial[pm->n] * pm->esize + snfft_workspace_bytes(pm, (int64_t)Bm) +
+           3 * (size_t)B * (size_t)pn->host.factorial[pn->n] * pn->esize;
+}
+
+int snfft_forward_cosets2(const snfft_plan_t* pn, const snfft_plan_t* pm, const void* f, int64_t B, const int* top,
+                          const int* sub, int npairs, void* F, void* ws, size_t ws_bytes, void* stream) {
+    if (!pn || !pm) return set_error(SNFFT_EINVAL, "plan is NULL");
+    if (pm->n != pn->n - 2 || pm->dtype != pn->dtype || pm->device != pn->device)
+        return set_error(SNFFT_EINVAL, "the second plan must be the S_{n-2} plan of the same dtype and device");
+    const int n = pn->n;
+    if (n < 4) return set_error(SNFFT_EINVAL, "two-level coset sharding needs n >= 4");
+    if (B < 0 || npairs < 0 || npairs > n * (n - 1)) return set_error(SNFFT_EINVAL, "bad batch or pair count");
+    if (B == 0) return SNFFT_OK;
+    if (!f || !F || (npairs && (!top || !sub))) return set_error(SNFFT_EINVAL, "NULL data pointer");
+    std::vector<char> seen((size_t)n * (n - 1), 0);
+    for (int j = 0; j < npairs; ++j) {
+        if (top[j] < 0 || top[j] >= n || sub[j] < 0 || sub[j] >= n - 1)
+            return set_error(SNFFT_EINVAL, "pairs must be (i_n in [0, n), i_{n-1} in [0, n-1))");
+        char& s = seen[(size_t)top[j] * (n - 1) + sub[j]];
+        if (s) return set_error(SNFFT_EINVAL, "duplicate two-level coset");
+        s = 1;
+    }
+    const size_t out_bytes = (size_t)B * (size_t)pn->host.factorial[n] * pn->esize;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (npairs == 0) {
+        SNFFT_CUDA(cudaMemsetAsync(F, 0, out_bytes, st));
+        return SNFFT_OK;
+    }
+    if ((long long)B * n * (n - 1) >= (1ll << 31)) return set_error(SNFFT_ENOTSUP, "batch too large for the pair slots");
+    if (!ws || ws_bytes < snfft_forward_cosets2_workspace_bytes(pn, pm, B, npairs))
+        return set_error(SNFFT_EWORKSPACE, "workspace too small");
+    return pn->dtype == SNFFT_F32 ? forward_cosets2_impl<float>(pn, pm, f, B, top, sub, npairs, F, ws, st)
+                                  : forward_cosets2_impl<double>(pn, pm, f, B, top, sub, npairs, F, ws, st);
+}
+
 int snfft_block_matmul(const snfft_plan_t* p, const void* A, const void* Bm, void* C, int64_t B, void* stream) {
     if (!p) return set_error(SNFFT_EINVAL, "plan is NULL");
     if (B < 0) return set_error(SNFFT_EINVAL, "negative batch");
@@ -1313,6 +1493,52 @@ int snfft_dense_rep(snfft_plan_t* p, int part, void* out, void* stream) {
         return set_error(SNFFT_ENOTSUP, "snfft_dense_rep: irrep too large for the dense cross-check");
     cudaStream_t st = (cudaStream_t)stream;
     return p->dtype == SNFFT_F32 ? dense_rep_impl<float>(p, part, out, st) : dense_rep_impl<double>(p, part, out, st);
+}
+
+static bool is_permutation(int n, const int* sigma) {
+    if (!sigma) return false;
+    bool seen[SNFFT_MAX_N] = {};
+    for (int i = 0; i < n; ++i) {
+        if (sigma[i] < 0 || sigma[i] >= n || seen[sigma[i]]) return false;
+        seen[sigma[i]] = true;
+    }
+    return true;
+}
+
+int snfft_rho(snfft_plan_t* p, int part, const int* sigma, void* out, void* stream) {
+    if (!p || !out) return set_error(SNFFT_EINVAL, "NULL plan or output");
+    const HostLevel& L = p->host.levels[p->n];
+    if (part < 0 || part >= (int)L.shapes.size()) return set_error(SNFFT_EINVAL, "bad partition index");
+    if (!is_permutation(p->n, sigma)) return set_error(SNFFT_EINVAL, "sigma is not a one-line permutation of range(n)");
+    cudaStream_t st = (cudaStream_t)stream;
+    return p->dtype == SNFFT_F32 ? rho_impl<float>(p, part, sigma, out, st) : rho_impl<double>(p, part, sigma, out, st);
+}
+
+int snfft_translate(int n, int dtype, const void* f, int64_t B, const int* perm, int right, void* out, void* stream) {
+    if (n < 1 || n > SNFFT_MAX_N) return set_error(SNFFT_EINVAL, "bad n");
+    if (dtype != SNFFT_F32 && dtype != SNFFT_F64) return set_error(SNFFT_EINVAL, "dtype must be 0 (f32) or 1 (f64)");
+    if (B < 0) return set_error(SNFFT_EINVAL, "negative batch");
+    if (!is_permutation(n, perm)) return set_error(SNFFT_EINVAL, "perm is not a one-line permutation of range(n)");
+    if (B == 0) return SNFFT_OK;
+    if (!f || !out || f == out) return set_error(SNFFT_EINVAL, "NULL data pointer or in-place translation");
+    TranslateArgs ta;
+    ta.ia = make_index_args(n);
+    ta.ia.batch = B;
+    ta.right = right ? 1 : 0;
+    for (int i = 0; i < SNFFT_MAX_N; ++i) ta.pinv[i] = 0;
+    for (int i = 0; i < n; ++i) ta.pinv[perm[i]] = i;
+    dim3 grid((unsigned)((ta.ia.nfact + 255) / 256), 1, 1), block(256, 1, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SNFFT_F32) {
+        auto kfn = translate_kernel<float>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const float*)f, (float*)out, ta);
+    } else {
+        auto kfn = translate_kernel<double>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const double*)f, (double*)out, ta);
+    }
+    g_launches.fetch_add(1);
+    SNFFT_CUDA(cudaGetLastError());
+    return SNFFT_OK;
 }
 
 int snfft_profile_begin(snfft_plan_t* p) {

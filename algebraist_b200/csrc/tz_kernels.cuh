@@ -8,8 +8,9 @@
 // (irreps.py:91-109) are FFMA immediates of straight-line code, lanes run over consecutive instances so every
 // global access is a contiguous run, every element of X_{k-1}, Z and X_k moves once per kernel that needs it.
 //
-// One translation unit per (kind, dtype, direction): SNFFT_TZ_KIND = 0 (Z kernel, shared by all levels) or the
-// level k of a T kernel.
+// Level 11 uses MB = 8 (level-8 column operators, three top sweeps like level 10).
+// One translation unit per (kind, dtype, direction): SNFFT_TZ_KIND = 7 / 8 (Z kernel with that MB, shared by the
+// levels that use it) or the level k = 9, 10, 11 of a T kernel.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -17,28 +18,31 @@
 #include <type_traits>
 
 #ifndef SNFFT_TZ_KIND
-#error "tz_kernels.cuh: define SNFFT_TZ_KIND (0 = Z kernel, 9 / 10 = T kernel of that level)"
+#error "tz_kernels.cuh: define SNFFT_TZ_KIND (7 / 8 = Z kernel with that MB, 9 / 10 / 11 = T kernel of that level)"
 #endif
 #include "tz_gen_tab.cuh"
-#if SNFFT_TZ_KIND == 0
+#if SNFFT_TZ_KIND == 7
 #include "tz_gen_z7.cuh"
+#elif SNFFT_TZ_KIND == 8
+#include "tz_gen_z8.cuh"
 #elif SNFFT_TZ_KIND == 9
 #include "tz_gen_t9.cuh"
 #elif SNFFT_TZ_KIND == 10
 #include "tz_gen_t10.cuh"
+#elif SNFFT_TZ_KIND == 11
+#include "tz_gen_t11.cuh"
 #endif
 
 namespace snfft {
 namespace {
 
-constexpr int TZ_MB = 7;
 constexpr int Z_THREADS = 128;
 constexpr int T_THREADS = 256;
-constexpr int Z_MAXGROUPS = 11;          // partitions of MB - 1 = 6
-constexpr int T_MAXTASKS = 256;
+constexpr int Z_MAXGROUPS = 15;          // partitions of MB - 1 = 6 (11) or 7 (15)
+constexpr int T_MAXTASKS = 512;
 
 // ---- Z kernel --------------------------------------------------------------------------------------------
-// A group is a shape zeta of S_6; its tasks are the parents alpha (forward) or the cosets i < 7 (inverse); its
+// A group is a shape zeta of S_{MB-1}; its tasks are the parents alpha (forward; MB = 8: x their child blocks) or the cosets i < MB (inverse); its
 // lanes are (segment, column c, instance): a segment is one piece (mu, path mu -> zeta) of level k-1.  Block
 // order inside a group as in col_kernels.cuh: `chunk` tiles of one task, then the same tiles of the next task,
 // so that the sibling tasks re-read their inputs from L2 while the CTAs of an SM share code.
@@ -56,7 +60,7 @@ struct ZGroups {
     unsigned long long lanes[Z_MAXGROUPS];       // units of the group * NINST_k
 };
 
-#if SNFFT_TZ_KIND == 0
+#if SNFFT_TZ_KIND == 7 || SNFFT_TZ_KIND == 8
 template <typename T, bool INV>
 __global__ void __launch_bounds__(Z_THREADS, (sizeof(T) == 4 ? 640 : 384) / Z_THREADS)
 z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, const ZGroups g, const ZSeg* __restrict__ segs,
@@ -90,8 +94,13 @@ z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, const ZGrou
     const size_t xo = ((size_t)sg.in_off + (size_t)c * (unsigned)g.k) * s + inst;
     const size_t zo = ((size_t)sg.z_off + c) * s + inst;
     const unsigned rs = (unsigned)sg.dmu * (unsigned)g.k * s, zs = (unsigned)sg.dmu * s;
+#if SNFFT_TZ_KIND == 7
     if constexpr (!INV) zb7f_run<T>(task, src + xo, dst + zo, rs, s, zs);
     else zb7i_run<T>(task, src + zo, dst + xo, rs, s, zs);
+#else
+    if constexpr (!INV) zb8f_run<T>(task, src + xo, dst + zo, rs, s, zs);
+    else zb8i_run<T>(task, src + zo, dst + xo, rs, s, zs);
+#endif
 }
 #endif
 
@@ -139,11 +148,10 @@ __host__ __device__ __forceinline__ TzVec<S, NV> operator-(const TzVec<S, NV>& a
 }
 struct TTasks {
     int ntasks;
-    unsigned blk0[T_MAXTASKS + 1];
-    unsigned short dal[T_MAXTASKS], dmu[T_MAXTASKS];
+    unsigned blk0[T_MAXTASKS + 1];       // first block of every task (d_alpha, d_mu per task: TzDev<K>, generated)
 };
 
-#if SNFFT_TZ_KIND != 0
+#if SNFFT_TZ_KIND >= 9
 // T = S (scalar threads) or TzVec<S, NV>; s = NINST_k / NV
 template <typename T, int K, bool INV>
 __global__ void __launch_bounds__(T_THREADS, 2)
@@ -157,8 +165,8 @@ t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::co
         else hi = mid - 1;
     }
     const int task = lo;
-    const unsigned dmu = g.dmu[task];
-    const unsigned long long qn = (unsigned long long)g.dal[task] * dmu * s;
+    const unsigned dmu = TzDev<K>::dmu(task);
+    const unsigned long long qn = (unsigned long long)TzDev<K>::dal(task) * dmu * s;
     const unsigned long long q = (unsigned long long)(b - g.blk0[task]) * T_THREADS + threadIdx.x;
     if (q >= qn) return;
     unsigned rc, inst;
@@ -170,17 +178,7 @@ t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::co
         inst = (unsigned)(q - (unsigned long long)rc * s);
     }
     const unsigned r = rc / dmu, c = rc - r * dmu;
-    if constexpr (K == 9) {
-#if SNFFT_TZ_KIND == 9
-        if constexpr (!INV) tz9f_run<T>(task, zb + inst, xb + inst, lb + inst, r, c, s);
-        else tz9i_run<T>(task, zb + inst, xb + inst, lb + inst, r, c, s);
-#endif
-    } else {
-#if SNFFT_TZ_KIND == 10
-        if constexpr (!INV) tz10f_run<T>(task, zb + inst, xb + inst, lb + inst, r, c, s);
-        else tz10i_run<T>(task, zb + inst, xb + inst, lb + inst, r, c, s);
-#endif
-    }
+    TzDev<K>::template run<T, INV>(task, zb + inst, xb + inst, lb + inst, r, c, s);
 }
 #endif
 

@@ -1,11 +1,11 @@
 // One translation unit per (kind, dtype, direction) of the top / bottom kernels (tz_kernels.cuh):
-//   -DSNFFT_TZ_KIND=0      Z kernel (level-7 column operators with run-time strides), every level
-//   -DSNFFT_TZ_KIND=9|10   T kernel of that level
+//   -DSNFFT_TZ_KIND=7|8        Z kernel (level-7 / level-8 column operators with run-time strides)
+//   -DSNFFT_TZ_KIND=9|10|11    T kernel of that level
 //   -DSNFFT_TZ_F64=0|1  -DSNFFT_TZ_INV=0|1
 // Exports (0 or a cudaError_t):
-//   int snfft_tz_z_<f32|f64>_<fwd|inv>(int k, const void* src, void* dst, long long ninst, stream)
-//        forward: src = X_{k-1}, dst = Z;  inverse: src = Z', dst = X_{k-1}
-//   int snfft_tz_z_prepare_<f32|f64>_<fwd|inv>(int k)        uploads the level's segment tables to the current device
+//   int snfft_tz_z<MB>_<f32|f64>_<fwd|inv>(int k, const void* src, void* dst, long long ninst, stream)
+//        forward: src = X_{k-1}, dst = Z;  inverse: src = Z', dst = X_{k-1};  k must be a level with that MB
+//   int snfft_tz_z<MB>_prepare_<f32|f64>_<fwd|inv>(int k)    uploads the level's segment tables to the current device
 //   int snfft_tz_t<k>_<f32|f64>_<fwd|inv>(void* z, void* x, void* xk, long long ninst, stream)
 //        forward: reads z, x (= X_{k-1}), writes xk (= X_k);  inverse: reads xk, writes z and the cosets i >= 7 of x
 #ifdef SNFFT_HOST_EMU
@@ -45,7 +45,7 @@ typedef float tz_t;
 namespace {
 using namespace snfft;
 
-#if SNFFT_TZ_KIND == 0
+#if SNFFT_TZ_KIND == 7 || SNFFT_TZ_KIND == 8
 constexpr int kMaxDev = 64;
 struct ZDev {                      // device copy of one level's segment tables
     ZSeg* segs = nullptr;
@@ -54,7 +54,7 @@ struct ZDev {                      // device copy of one level's segment tables
     unsigned units[Z_MAXGROUPS] = {};
     bool ready = false;
 };
-ZDev g_zdev[kMaxDev][2];           // [device][k - 9]
+ZDev g_zdev[kMaxDev][3];           // [device][k - 9]
 std::mutex g_zmu;
 
 template <int K>
@@ -90,7 +90,11 @@ int z_upload(ZDev& d) {
 }
 
 int z_tables(int k, ZDev** out) {
+#if SNFFT_TZ_KIND == 7
     if (k != 9 && k != 10) return (int)cudaErrorInvalidValue;
+#else
+    if (k != 11) return (int)cudaErrorInvalidValue;
+#endif
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
@@ -98,7 +102,11 @@ int z_tables(int k, ZDev** out) {
     std::lock_guard<std::mutex> lock(g_zmu);
     ZDev& d = g_zdev[dev][k - 9];
     if (!d.ready) {
+#if SNFFT_TZ_KIND == 7
         const int rc = k == 9 ? z_upload<9>(d) : z_upload<10>(d);
+#else
+        const int rc = z_upload<11>(d);
+#endif
         if (rc) return rc;
     }
     *out = &d;
@@ -108,10 +116,15 @@ int z_tables(int k, ZDev** out) {
 
 }  // namespace
 
-#if SNFFT_TZ_KIND == 0
+#if SNFFT_TZ_KIND == 7 || SNFFT_TZ_KIND == 8
 
-#define TZ_ZNAME TZ_CAT3(snfft_tz_z_, TZ_DT, TZ_DIR)
-#define TZ_ZPREP TZ_CAT3(snfft_tz_z_prepare_, TZ_DT, TZ_DIR)
+#if SNFFT_TZ_KIND == 7
+#define TZ_ZNAME TZ_CAT3(snfft_tz_z7_, TZ_DT, TZ_DIR)
+#define TZ_ZPREP TZ_CAT3(snfft_tz_z7_prepare_, TZ_DT, TZ_DIR)
+#else
+#define TZ_ZNAME TZ_CAT3(snfft_tz_z8_, TZ_DT, TZ_DIR)
+#define TZ_ZPREP TZ_CAT3(snfft_tz_z8_prepare_, TZ_DT, TZ_DIR)
+#endif
 
 extern "C" int TZ_ZPREP(int k) {
     ZDev* d = nullptr;
@@ -128,10 +141,11 @@ extern "C" int TZ_ZNAME(int k, const void* src, void* dst, long long ninst, cuda
     ZDev* d = nullptr;
     int rc = z_tables(k, &d);
     if (rc) return rc;
-    using I = ZInfo<SNFFT_TZ_INV != 0>;
+    using I = ZInfo<SNFFT_TZ_KIND, SNFFT_TZ_INV != 0>;
     static_assert(I::ngroups <= Z_MAXGROUPS, "too many groups");
-    // 32-bit strides: row stride d_mu k NINST of X_{k-1} (d_mu <= 216 at k = 10)
-    if (ninst <= 0 || (unsigned long long)ninst * 216ull * (unsigned long long)k >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    // 32-bit strides: row stride d_mu k NINST of X_{k-1} (d_mu <= 216 at k = 10, <= 768 at k = 11)
+    if (ninst <= 0 || (unsigned long long)ninst * (k == 11 ? 768ull : 216ull) * (unsigned long long)k >= (1ull << 32))
+        return (int)cudaErrorInvalidValue;
     ZGroups g;
     g.ngroups = I::ngroups;
     g.chunk = chunk < 1 ? 1 : chunk;
@@ -180,8 +194,6 @@ extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_
     unsigned long long blk = 0;
     for (int t = 0; t < L::ntasks; ++t) {
         g.blk0[t] = (unsigned)blk;
-        g.dal[t] = (unsigned short)L::t_dal()[t];
-        g.dmu[t] = (unsigned short)L::t_dmu()[t];
         const unsigned long long q = (unsigned long long)L::t_dal()[t] * L::t_dmu()[t] * (unsigned long long)ninst;
         blk += (q + T_THREADS - 1) / T_THREADS;
     }

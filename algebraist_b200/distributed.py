@@ -67,6 +67,14 @@ def coset_shards(n: int, world_size: int):
     return [shard_bounds(n, world_size, r) for r in range(world_size)]
 
 
+def coset_pair_shards(n: int, world_size: int):
+    """The n (n-1) two-level cosets (i_n, i_{n-1}) -- sigma[i_n] = n-1 and, inside that coset, value n-2 at
+    position i_{n-1} -- dealt to the ranks as contiguous runs of the (i_n major) list whose sizes differ by at
+    most one: 110 units at n = 11, i.e. 14 / 13 per rank on 8 GPUs instead of 2 / 1 top-level cosets."""
+    pairs = [(i, j) for i in range(n) for j in range(n - 1)]
+    return [pairs[lo:hi] for lo, hi in (shard_bounds(len(pairs), world_size, r) for r in range(world_size))]
+
+
 def partition_owners(dims, world_size: int):
     """Which rank ends up with which partition after the reduce-scatter.
 
@@ -122,17 +130,59 @@ def sn_fft_coset_partial(fn_vals: torch.Tensor, n: int, cosets):
     return plan, packed, batch
 
 
-def sn_fft_coset_sharded(fn_vals: torch.Tensor, n: int, group=None) -> dict:
-    """Forward transform of one large function (or a small batch) that every rank holds, sharded over the
-    top-level cosets: rank r transforms the restrictions of f to its cosets (S_{n-1} sub-transforms), applies
-    its terms of the level-n step, and one sum reduce-scatter over the packed coefficients leaves every rank
-    with a subset of the partitions.  Returns {partition: F(partition)} for the partitions THIS rank owns
-    (shapes as sn_fft); `partition_owners` tells which rank has which."""
+def sn_fft_coset2_partial(fn_vals: torch.Tensor, n: int, pairs):
+    """The terms of the two top Clausen sums (fourier.py:253-273 applied at levels n and n-1) that the two-level
+    cosets `pairs` = [(i_n, i_{n-1}), ...] own, as a packed coefficient tensor plus the plan: the pairs'
+    restrictions run through the S_{n-2} pipeline as one batch and the last two level steps run on their
+    (otherwise zero) level array."""
+    from . import _lib
+    from .fourier import _check_input, _device_ctx, _stream_ptr, _to_device
+    from .plan import get_plan
+    import ctypes
+    _check_input(fn_vals, n)
+    if n < 4:
+        raise ValueError("two-level coset sharding needs n >= 4")
+    x, _ = _to_device(fn_vals)
+    f2d = x.reshape(-1, x.shape[-1]).contiguous()
+    batch = f2d.shape[0]
+    pairs = sorted((int(i), int(j)) for i, j in pairs)
+    plan = get_plan(n, f2d.dtype, f2d.device)
+    sub = get_plan(n - 2, f2d.dtype, f2d.device)
+    packed = torch.empty(batch * plan.nfact, dtype=f2d.dtype, device=f2d.device)
+    if batch:
+        lib = _lib.load()
+        top = (ctypes.c_int * max(len(pairs), 1))(*[i for i, _ in pairs])
+        low = (ctypes.c_int * max(len(pairs), 1))(*[j for _, j in pairs])
+        with _device_ctx(f2d.device):
+            nbytes = lib.snfft_forward_cosets2_workspace_bytes(plan.handle, sub.handle, batch, len(pairs))
+            ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=f2d.device)
+            _lib.check(lib.snfft_forward_cosets2(plan.handle, sub.handle, f2d.data_ptr(), batch, top, low, len(pairs),
+                                                 packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(f2d.device)),
+                       "snfft_forward_cosets2")
+    return plan, packed, batch
+
+
+def sn_fft_coset_sharded(fn_vals: torch.Tensor, n: int, group=None, levels: int = None) -> dict:
+    """Forward transform of one large function (or a small batch) that every rank holds, sharded over cosets:
+    rank r transforms the restrictions of f to its cosets, applies its terms of the top level steps, and one sum
+    reduce-scatter over the packed coefficients leaves every rank with a subset of the partitions.  Returns
+    {partition: F(partition)} for the partitions THIS rank owns (shapes as sn_fft); `partition_owners` tells
+    which rank has which.
+
+    levels = 2 (default for n >= 4): the units are the n (n-1) two-level cosets (`coset_pair_shards`, S_{n-2}
+    sub-transforms); levels = 1: the n top-level cosets (`coset_shards`, S_{n-1} sub-transforms)."""
     if not dist.is_initialized():
         raise RuntimeError("sn_fft_coset_sharded needs an initialised torch.distributed process group")
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    lo, hi = coset_shards(n, world)[rank]
-    plan, packed, batch = sn_fft_coset_partial(fn_vals, n, range(lo, hi))
+    if levels is None:
+        levels = 2 if n >= 4 else 1
+    if levels == 2:
+        plan, packed, batch = sn_fft_coset2_partial(fn_vals, n, coset_pair_shards(n, world)[rank])
+    elif levels == 1:
+        lo, hi = coset_shards(n, world)[rank]
+        plan, packed, batch = sn_fft_coset_partial(fn_vals, n, range(lo, hi))
+    else:
+        raise ValueError("levels must be 1 or 2")
     owner, bin_size = partition_owners(plan.dims, world)
     # send buffer [world][bin_size * batch]: the partitions of bin r back to back, zero padded (one batched copy)
     pieces, slots, fill = [[] for _ in range(world)], {}, [0] * world

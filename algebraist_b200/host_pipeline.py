@@ -85,14 +85,20 @@ def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, ch
     out_ready = [None] * nslots                        # the transform that produced slot s finished
     out_free = [None] * nslots                         # copy-out of slot s finished
     start = torch.cuda.Event()
-    start.record(compute)
-    s_in.wait_event(start)                             # src_host may have been produced by work queued on `compute`
     sizes = chunk_schedule(batch, chunk, ramp)
     bounds = [0]
     for m in sizes:
         bounds.append(bounds[-1] + m)
     nchunks = len(sizes)
     cmax = max(sizes)
+    # The chunk buffers come from the CURRENT stream's pool of the caching allocator (s_in only starts after
+    # `start`, and the call returns after every copy has finished), so repeated calls reuse the same blocks.
+    # Allocated under s_in they would belong to a stream that changes from call to call: every call would
+    # cudaMalloc its buffers again (profiles r02c: single steps of 100-250 ms).
+    for s in range(min(nslots, nchunks)):
+        ins[s] = torch.empty((cmax,) + tuple(src_host.shape[1:]), dtype=src_host.dtype, device=dev)
+    start.record(compute)
+    s_in.wait_event(start)                             # src_host may have been produced by work queued on `compute`
 
     def copy_in(c):
         s = c % nslots
@@ -100,8 +106,6 @@ def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, ch
         with torch.cuda.stream(s_in):
             if in_free[s] is not None:
                 s_in.wait_event(in_free[s])
-            if ins[s] is None:
-                ins[s] = torch.empty((cmax,) + tuple(src_host.shape[1:]), dtype=src_host.dtype, device=dev)
             ins[s][:hi - lo].copy_(src_host[lo:hi], non_blocking=True)
             in_ready[s] = torch.cuda.Event()
             in_ready[s].record(s_in)
@@ -117,7 +121,11 @@ def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, ch
         if out_free[s] is not None:
             compute.wait_event(out_free[s])            # the previous result in this slot has left the device
         res = fn(ins[s][:hi - lo])
-        outs[s] = res                                  # keeps the result alive until its copy has been queued
+        # The result stays referenced until this slot is reused, and the compute stream waits for the slot's
+        # copy-out (out_free) before that, so the block is never handed out again while s_out still reads it:
+        # no record_stream (its deferred frees made the caching allocator fall back to cudaMalloc at random
+        # points of the pipeline: single steps of 100-250 ms, profiles r02c).
+        outs[s] = res
         in_free[s] = torch.cuda.Event()
         in_free[s].record(compute)
         out_ready[s] = torch.cuda.Event()
@@ -127,7 +135,6 @@ def stream_batches(fn, src_host: torch.Tensor, dst_host: torch.Tensor = None, ch
         with torch.cuda.stream(s_out):
             s_out.wait_event(out_ready[s])
             dst_host[lo:hi].copy_(res, non_blocking=True)
-            res.record_stream(s_out)
             out_free[s] = torch.cuda.Event()
             out_free[s].record(s_out)
     s_out.synchronize()

@@ -150,6 +150,33 @@ int snfft_forward_cosets(const snfft_plan_t* plan_n, const snfft_plan_t* plan_nm
                          void* stream);
 
 /*
+ * The same partial transform over a subset of the n (n-1) TWO-level cosets
+ * (sigma[top[j]] = n-1, and the restriction to that coset has value n-2 at
+ * position sub[j]: restrict_to_coset applied twice, fourier.py:63-80,253):
+ * finer units of work for sharding ONE function over 8 GPUs than the n
+ * top-level cosets.  plan_nm2 is the S_{n-2} plan of the same dtype and
+ * device; pairs must be distinct; npairs == 0 writes zeros.  The partial
+ * results of a partition of all pairs add up to the full transform.
+ */
+size_t snfft_forward_cosets2_workspace_bytes(const snfft_plan_t* plan_n, const snfft_plan_t* plan_nm2, int64_t B,
+                                             int npairs);
+int snfft_forward_cosets2(const snfft_plan_t* plan_n, const snfft_plan_t* plan_nm2, const void* f, int64_t B,
+                          const int* top, const int* sub, int npairs, void* F, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/*
+ * Group-action utilities on the device.
+ *   rho       : out[d][d] (row major, device) = rho_lambda(sigma) in Young's orthogonal form for the partition
+ *               with index `part` of the plan's level n, sigma a one-line permutation of range(n) (host array)
+ *               -- SnIrrep.matrix_representations[sigma], irreps.py:122-141; any dimension
+ *   translate : out[b][k] = f[b][rank(perm^-1 * p_k)] (right == 0, the left translation of
+ *               tests/test_fourier.py:112-121) or f[b][rank(p_k * perm^-1)] (right != 0); p_k = the k-th
+ *               permutation in lexicographic order, (a * b)[i] = b[a[i]] (permutations.py:85-88).  f != out.
+ */
+int snfft_rho(snfft_plan_t* plan, int part, const int* sigma, void* out, void* stream);
+int snfft_translate(int n, int dtype, const void* f, int64_t B, const int* perm, int right, void* out, void* stream);
+
+/*
  * Same transforms with HOST buffers (pageable or pinned): copies in, runs the
  * device pipeline, copies out, and returns after the result is in `F_host` /
  * `f_host`.  Scratch is owned by the plan and grows on demand.

@@ -1,0 +1,6 @@
+TAG=$1
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/pytest_gpu_$TAG.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+tail -3 gpurun_out/bench_$TAG.err
+python tools/show_bench.py gpurun_out/bench_$TAG.json
