@@ -91,8 +91,11 @@ def stale(target, deps):
 
 
 def needs_build() -> bool:
+    """The library is up to date when it is newer than every source it was built from; the object cache under
+    _obj/ only matters for an incremental rebuild (it does not travel to the GPU box: .gpurunignore)."""
     generate_col_headers()
-    return any(stale(o, d) for o, _, _, d in units()) or stale(OUT, [o for o, _, _, _ in units()])
+    deps = sorted({d for _, _, _, ds in units() for d in ds})
+    return stale(OUT, deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

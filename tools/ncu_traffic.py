@@ -3,7 +3,7 @@ tools/prof_step.py (tools/ncu_summary.py): DRAM read + write bytes per launch of
 line names.  The level kernels of one forward + inverse run in a fixed order, so the k-th launch of a
 kernel family is matched to the bench name by its template arguments and grid.
 
-    python tools/ncu_traffic.py summary.csv batch dtype out.json
+    python tools/ncu_traffic.py summary.csv batch dtype out.json [n]
 """
 import csv
 import json
@@ -31,15 +31,41 @@ def main():
         for k in (6, 7, 8):
             fam[f"col_kernel<{t}, {k}, 0>"] = f"fwd_level_k{k}_c-3"
             fam[f"col_kernel<{t}, {k}, 1>"] = f"inv_level_k{k}_c-3"
+    # top / bottom kernels: the T kernel names its level and direction; the Z kernel (level-7 operators) runs for
+    # k = 9 and 10 in a fixed order inside one forward + inverse: forward 9, forward 10, inverse 10, inverse 9
+    for t in ("float", "double"):
+        for k in (9, 10, 11):
+            for pat_t in (t, f"TzVec<{t}, 4>", f"TzVec<{t}, 2>"):
+                fam[f"t_kernel<{pat_t}, {k}, 0>"] = f"fwd_level_k{k}_c-5"
+                fam[f"t_kernel<{pat_t}, {k}, 1>"] = f"inv_level_k{k}_c-5"
+    zorder = {"0": ["fwd_level_k9_c-4", "fwd_level_k10_c-4"], "1": ["inv_level_k10_c-4", "inv_level_k9_c-4"]}
+    zseen = {"0": 0, "1": 0}
     best = {}
     for r in rows[1:]:
+        if "z_kernel<" in r[ki]:
+            inv = "1" if (", 1>" in r[ki] or "true>" in r[ki]) else "0"
+            if zseen[inv] < len(zorder[inv]):
+                name = zorder[inv][zseen[inv]]
+                zseen[inv] += 1
+                best[name] = (float(r[ti].split()[0]), to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
+            continue
         for pat, name in fam.items():
-            if r[ki].startswith(pat) or ("col_kernel" in pat and pat in r[ki]):
+            if r[ki].startswith(pat) or (("col_kernel" in pat or "t_kernel" in pat) and pat in r[ki]):
                 t = float(r[ti].split()[0])
                 if name not in best or t > best[name][0]:
                     best[name] = (t, to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
+    import os
+    import subprocess
+    try:
+        commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
+                                cwd=os.path.dirname(os.path.abspath(__file__))).stdout.strip() or None
+    except OSError:
+        commit = None
+    commit = os.environ.get("SNFFT_COMMIT", commit)
+    n = int(sys.argv[5]) if len(sys.argv) > 5 else 10
     for name, (t, b, ts) in best.items():
-        recs.append({"kernel": name, "batch": batch, "dtype": dtype, "dram_bytes_per_launch": b, "ncu_time": ts})
+        recs.append({"kernel": name, "n": n, "batch": batch, "dtype": dtype, "dram_bytes_per_launch": b, "ncu_time": ts,
+                     "capture": os.path.basename(sys.argv[1]), "commit": commit})
     json.dump(recs, open(out, "w"), indent=1)
     print(recs)
 
