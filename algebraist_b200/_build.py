@@ -18,8 +18,7 @@ OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libsnfft_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "snfft.h")
 
-MAIN_DEPS = [os.path.join(CSRC, f) for f in ("snfft.cu", "kernels.cuh", "plan.h", "level_tb.cuh", "bot_gen.cuh",
-                                             "base_gen.cuh", "tb_host.inl")] + [HEADER]
+MAIN_DEPS = [os.path.join(CSRC, f) for f in ("snfft.cu", "kernels.cuh", "plan.h", "base_gen.cuh")] + [HEADER]
 PLAN_DEPS = [os.path.join(CSRC, f) for f in ("plan.cpp", "plan.h")]
 def col_deps(k):
     return [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", f"col_gen_{k}.cuh")]

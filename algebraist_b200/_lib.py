@@ -49,6 +49,11 @@ SIGNATURES = {
                                       ctypes.c_size_t, c_vp]),
     "snfft_forward_cosets": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_int), c_int, c_vp, c_vp, ctypes.c_size_t,
                                      c_vp]),
+    "snfft_subplan_create": (c_int, [c_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(c_vp)]),
+    "snfft_subplan_destroy": (None, [c_vp]),
+    "snfft_subplan_info": (c_int, [c_vp, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double)]),
+    "snfft_forward_subset": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "snfft_inverse_subset": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "snfft_power": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "snfft_block_matmul": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "snfft_forward_host": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -11,7 +11,7 @@ and the +-1 rows cost nothing, and nothing touches shared memory.
 
 Generated device functions (T = float / double):
   s5_forward / s5_inverse   levels 2..5 (5..2) of one S_5 instance, 120 values in registers
-  l6_forward / l6_inverse   level 6 (one S_6 instance per thread), global -> global
+(level 6 and above: gen_col.py, gen_tz.py, which import the combinatorics below)
 
 The combinatorics below restate the reference's conventions (partition order
 tableau.py:103-123, children irreps.py:64-68, basis order tableau.py:171-198,
@@ -334,75 +334,6 @@ def gen_s5(forward):
     return "\n".join(head + em.lines + ["}"]) + "\n", em.n
 
 
-def gen_l6(forward):
-    """Level 6, one S_6 instance per thread, straight from / to global memory.
-    in / out point at this thread's instance; element e of the level-6 array is at e * s6 and element
-    (e5, coset i) of the level-5 array at (e5 * 6 + i) * s6, s6 = NINST_6.
-    One __noinline__ function per output partition keeps every function small enough for ptxas."""
-    k = 6
-    funcs, calls = [], []
-    total = 0
-    name = "l6_forward" if forward else "l6_inverse"
-    groups = partitions(k - 1)
-    for g, part in enumerate(groups):
-        body = []
-        if forward:
-            # child-major: the 6 * d_mu inputs of column c of F_mu are loaded once and shared by every
-            # parent lambda of mu (loading them per parent re-read each child 2.6 times from DRAM)
-            mu = part
-            for c in range(dim(mu)):
-                em = ScaledEmitter()
-                cache = {}
-
-                def load(m, r, cc, i, em=em, cache=cache):
-                    key = (m, r, cc, i)
-                    if key not in cache:
-                        e5 = coef_off(m) + r * dim(m) + cc
-                        cache[key] = em.tmp(f"in[(size_t){e5 * 6 + i} * s6]")
-                    return cache[key]
-
-                def store(l, t, col, v, em=em):
-                    e6 = coef_off(l) + t * dim(l) + col
-                    em.lines.append(f"    out[(size_t){e6} * s6] = {value_expr(v)};")
-
-                # issue every load of the column first (memory-level parallelism)
-                for r in range(dim(mu)):
-                    for i in range(k):
-                        load(mu, r, c, i)
-                for lam in partitions(k):
-                    if mu in children(lam):
-                        forward_column(em, k, lam, children(lam).index(mu), c, load, store)
-                body.append("  {\n" + "\n".join(em.lines) + "\n  }\n  SNFFT_CODE_FENCE();")
-                total += em.n
-        else:
-            mu = part
-            for c in range(dim(mu)):
-                for i in range(k):
-                    em = ScaledEmitter()
-
-                    def load(l, t, col, em=em):
-                        e6 = coef_off(l) + t * dim(l) + col
-                        return em.tmp(f"in[(size_t){e6} * s6]")
-
-                    def store(m, r, cc, v, em=em, i=i):
-                        e5 = coef_off(m) + r * dim(m) + cc
-                        em.lines.append(f"    out[(size_t){e5 * 6 + i} * s6] = {value_expr(v)};")
-
-                    inverse_column(em, k, mu, c, i, load, store)
-                    body.append("  {\n" + "\n".join(em.lines) + "\n  }\n  SNFFT_CODE_FENCE();")
-                    total += em.n
-        funcs.append("\n".join([
-            "template <typename T>",
-            f"__device__ __noinline__ void {name}_part{g}(const T* __restrict__ in, T* __restrict__ out, size_t s6) {{"]
-            + body + ["}"]) + "\n")
-        calls.append(f"    {name}_part{g}<T>(in, out, s6);")
-    funcs.append("\n".join([
-        "template <typename T>",
-        f"__device__ __forceinline__ void {name}(const T* __restrict__ in, T* __restrict__ out, size_t s6) {{"]
-        + calls + ["}"]) + "\n")
-    return "\n".join(funcs), total
-
-
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
     parts = ["// GENERATED by gen_base.py -- do not edit.  Straight-line Young's-orthogonal-form code for the",
@@ -412,7 +343,7 @@ def main():
              "// (otherwise the register allocator sees every column of the level at once and spills)",
              "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")", "", "namespace snfft {", ""]
     stats = {}
-    for fn, fwd in ((gen_s5, True), (gen_s5, False), (gen_l6, True), (gen_l6, False)):
+    for fn, fwd in ((gen_s5, True), (gen_s5, False)):
         code, n = fn(fwd)
         stats[(fn.__name__, fwd)] = n
         parts.append(code)

@@ -522,143 +522,10 @@ __global__ void __launch_bounds__(W* G* NG, MINB) inv_level_kernel(const LevelAr
 }
 
 // ---------------------------------------------------------------------------
-// fused base kernels: levels 2..K0 (forward) / K0..2 (inverse) in shared memory.
-// A CTA owns TI consecutive level-K0 instances (one per lane); inside the tile a
-// level-k array is laid out like the global one with NINST replaced by P_k * TI,
-// P_k = K0!/k!:  element (coef e, chain p, lane) at (e * P_k + p) * TI + lane,
-// and the k cosets are the planes p_{k-1} = i * P_k + p.  Work items (task,
-// column c, chain p) are dealt to warps; every lane transforms its own instance,
-// so only level boundaries need a barrier.  One global read and one global write
-// replace K0-1 level passes.
-// ---------------------------------------------------------------------------
-template <typename T>
-struct BaseLevel {
-    const FwdTask* ftasks;
-    const InvTask* itasks;
-    const InvParent* parents;
-    const uint32_t* tables;
-    int nftasks, nitasks, tab_words, pad;
-    T lut[2 * LUT];
-};
-
-constexpr int BASE_MAXK = 6;
-
-template <typename T>
-struct BaseArgs {
-    const T* in;
-    T* out;
-    long long ninst;                  // NINST_{K0}
-    int k0, tab_smem_words;
-    long long fact[BASE_MAXK + 1];
-    BaseLevel<T> lev[BASE_MAXK + 1];  // lev[k], k = 2..k0
-};
-
-template <typename T, int TI, int NW, int DMAXB>
-__host__ __device__ inline size_t base_smem_bytes(int k0fact, int tab_words) {
-    return ((size_t)2 * k0fact * TI + (size_t)NW * DMAXB * TI + 2 * LUT) * sizeof(T) + (size_t)tab_words * sizeof(uint32_t);
-}
-
-template <typename T, int TI, int NW, int DMAXB, bool INVERSE>
-__global__ void __launch_bounds__(NW * 32) base_kernel(const BaseArgs<T> a) {
-    SNFFT_DYN_SMEM(smem_raw);
-    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-    const int k0 = a.k0;
-    const int nf = (int)a.fact[k0];
-    T* bufA = reinterpret_cast<T*>(smem_raw);
-    T* bufB = bufA + (size_t)nf * TI;
-    T* scratch = bufB + (size_t)nf * TI + (size_t)warp * DMAXB * TI;
-    T* lut = bufB + (size_t)nf * TI + (size_t)NW * DMAXB * TI;
-    uint32_t* tab_s = reinterpret_cast<uint32_t*>(lut + 2 * LUT);
-    const long long i0 = (long long)blockIdx.x * TI;
-    const bool lane_ok = lane < TI;
-    const bool valid = lane_ok && i0 + lane < a.ninst;
-
-    // tile in: X_1 (forward) or X_{K0} (inverse); both are [K0!][NINST_{K0}] instance fastest
-    if (lane_ok)
-        for (int e = warp; e < nf; e += NW) bufA[e * TI + lane] = valid ? a.in[(long long)e * a.ninst + i0 + lane] : T(0);
-
-    T* cur = bufA;
-    T* nxt = bufB;
-    for (int step = 0; step < k0 - 1; ++step) {
-        const int k = INVERSE ? k0 - step : 2 + step;
-        const BaseLevel<T>& L = a.lev[k];
-        const int pk = (int)(a.fact[k0] / a.fact[k]);       // P_k
-        __syncthreads();                                    // previous level done, old table free
-        for (int w = tid; w < L.tab_words; w += NW * 32) tab_s[w] = L.tables[w];
-        if (tid < 2 * LUT) lut[tid] = L.lut[(tid & 1) * LUT + (tid >> 1)];
-        __syncthreads();
-        if (!INVERSE) {
-            for (int t = 0; t < L.nftasks; ++t) {
-                const FwdTask tk = L.ftasks[t];
-                const uint32_t* tab = tab_s + tk.tab_off;
-                const int nitems = tk.d_mu * pk;
-                for (int q = warp; q < nitems; q += NW) {
-                    if (!lane_ok) continue;
-                    const int c = q / pk, p = q % pk;
-                    T acc[DMAXB];
-#pragma unroll
-                    for (int r = 0; r < DMAXB; ++r) acc[r] = T(0);
-                    for (int i = 0; i < k; ++i) {
-                        for (int r = 0; r < tk.d_lam; ++r) scratch[r * TI + lane] = T(0);
-                        for (int r = 0; r < tk.d_mu; ++r)
-                            scratch[(tk.boff + r) * TI + lane] =
-                                cur[((int)(tk.mu_off + r * tk.d_mu + c) * (pk * k) + i * pk + p) * TI + lane];
-                        for (int j = k - 2; j >= i; --j) sweep<T, 1, TI, 1, 1>(scratch, 0, 1, tab, lut, k, j, 0, lane);
-#pragma unroll
-                        for (int r = 0; r < DMAXB; ++r)
-                            if (r < tk.d_lam) acc[r] += scratch[r * TI + lane];
-                    }
-#pragma unroll
-                    for (int r = 0; r < DMAXB; ++r)
-                        if (r < tk.d_lam)
-                            nxt[((int)(tk.lam_off + r * tk.d_lam + tk.boff + c) * pk + p) * TI + lane] = acc[r];
-                }
-            }
-        } else {
-            for (int t = 0; t < L.nitasks; ++t) {
-                const InvTask tk = L.itasks[t];
-                const int nitems = tk.d_mu * pk * k;
-                for (int q = warp; q < nitems; q += NW) {
-                    if (!lane_ok) continue;
-                    const int i = q % k, cp = q / k;
-                    const int c = cp / pk, p = cp % pk;
-                    T acc[DMAXB];
-#pragma unroll
-                    for (int r = 0; r < DMAXB; ++r) acc[r] = T(0);
-                    for (int pp = 0; pp < tk.npar; ++pp) {
-                        const InvParent par = L.parents[tk.par_off + pp];
-                        const uint32_t* tab = tab_s + par.tab_off;
-                        for (int r = 0; r < par.d_lam; ++r)
-                            scratch[r * TI + lane] =
-                                cur[((int)(par.lam_off + r * par.d_lam + par.boff + c) * pk + p) * TI + lane];
-                        for (int j = i; j <= k - 2; ++j) sweep<T, 1, TI, 1, 1>(scratch, 0, 1, tab, lut, k, j, 0, lane);
-                        const T scale = (T)par.scale;
-#pragma unroll
-                        for (int r = 0; r < DMAXB; ++r)
-                            if (r < tk.d_mu) acc[r] += scale * scratch[(par.boff + r) * TI + lane];
-                    }
-#pragma unroll
-                    for (int r = 0; r < DMAXB; ++r)
-                        if (r < tk.d_mu)
-                            nxt[((int)(tk.mu_off + r * tk.d_mu + c) * (pk * k) + i * pk + p) * TI + lane] = acc[r];
-                }
-            }
-        }
-        T* sw = cur;
-        cur = nxt;
-        nxt = sw;
-    }
-    __syncthreads();
-    if (valid)
-        for (int e = warp; e < nf; e += NW) a.out[(long long)e * a.ninst + i0 + lane] = cur[e * TI + lane];
-}
-
-// ---------------------------------------------------------------------------
 // generated register kernels for the lowest levels (base_gen.cuh, gen_base.py):
 // one instance per thread, lanes over consecutive instances so every global
 // access is a contiguous 128-byte row.
 //   s5_kernel : X_1 [120][NINST_5] -> X_5 [120][NINST_5]   (levels 2..5; inverse: 5..2)
-//   l6_kernel : X_5 [120*6][NINST_6] -> X_6 [720][NINST_6] (level 6; inverse: 6)
 // ---------------------------------------------------------------------------
 constexpr int GEN_THREADS = 128;
 
@@ -673,14 +540,6 @@ __global__ void __launch_bounds__(GEN_THREADS) s5_kernel(const T* __restrict__ i
     else s5_forward<T>(x, y);
 #pragma unroll
     for (int e = 0; e < 120; ++e) out[(size_t)e * ninst5 + inst] = y[e];
-}
-
-template <typename T, bool INVERSE>
-__global__ void __launch_bounds__(GEN_THREADS) l6_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst6) {
-    const long long inst = (long long)blockIdx.x * GEN_THREADS + threadIdx.x;
-    if (inst >= ninst6) return;
-    if (INVERSE) l6_inverse<T>(in + inst, out + inst, (size_t)ninst6);
-    else l6_forward<T>(in + inst, out + inst, (size_t)ninst6);
 }
 
 // ---------------------------------------------------------------------------
@@ -855,13 +714,15 @@ __global__ void __launch_bounds__(GS_THREADS) gather_kernel(const T* __restrict_
     SNFFT_DYN_SMEM(smem_raw);
     long long* p1 = reinterpret_cast<long long*>(smem_raw);
     T* tile = reinterpret_cast<T*>(smem_raw + GS_TR * sizeof(long long));
-    const long long r0 = (long long)blockIdx.x * GS_TR, b0 = (long long)blockIdx.y * GS_TB;
+    const long long r0 = (long long)blockIdx.x * GS_TR;
     const int tid = threadIdx.x;
     if (tid < GS_TR) {
         const long long r = r0 + tid;
         p1[tid] = r < ia.nfact ? chain_index(ia.n, r, ia.fact) : -1;
     }
-    if (SCATTER) __syncthreads();
+    __syncthreads();
+    // batch tiles with a grid stride: grid.y is capped at 65535 (any batch size works)
+    for (long long b0 = (long long)blockIdx.y * GS_TB; b0 < ia.batch; b0 += (long long)gridDim.y * GS_TB) {
     if (!SCATTER) {
         for (int e = tid; e < GS_TB * GS_TR; e += GS_THREADS) {
             const int bb = e / GS_TR, rr = e % GS_TR;
@@ -888,6 +749,8 @@ __global__ void __launch_bounds__(GS_THREADS) gather_kernel(const T* __restrict_
             if (b0 + bb < ia.batch && r0 + rr < ia.nfact)
                 out[(b0 + bb) * ia.nfact + r0 + rr] = tile[bb * (GS_TR + 1) + rr];
         }
+    }
+    __syncthreads();            // the tile is reused by the next batch tile
     }
 }
 
@@ -984,27 +847,52 @@ __global__ void __launch_bounds__(256) gather_vec_kernel(const T* __restrict__ i
 // calc_power (fourier.py:362-393): power[lambda][b] = d_lambda / n! * || F_lambda[b] ||_F^2 on the packed
 // coefficients [lambda][B][d][d].   grid (partitions, B), 256 threads, fp64 accumulation
 // ---------------------------------------------------------------------------
+// Sum over the 256 threads of a CTA: warp-shuffle tree inside each warp, one shared-memory word per warp, then the
+// first warp.  (The host-emulation build runs one fiber per thread and has no shuffles: plain shared-memory tree.)
+__device__ __forceinline__ double block_sum_256(double v, double* part) {
+#ifdef SNFFT_HOST_EMU
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+        __syncthreads();
+    }
+    const double r = part[0];
+    __syncthreads();
+    return r;
+#else
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) part[warp] = v;
+    __syncthreads();
+    v = lane < 8 ? part[lane] : 0.0;
+    if (warp == 0)
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) part[0] = v;
+    __syncthreads();
+    const double r = part[0];
+    __syncthreads();
+    return r;
+#endif
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) power_kernel(const T* __restrict__ F, const long long* __restrict__ coef_off,
                                                    const int* __restrict__ dims, long long batch, double inv_order,
                                                    T* __restrict__ out) {
     __shared__ double part[256];
     const int lam = blockIdx.x;
-    const long long b = blockIdx.y;
     const long long lo = coef_off[lam], dd = coef_off[lam + 1] - lo;
-    const T* __restrict__ src = F + lo * batch + b * dd;
-    double acc = 0.0;
-    for (long long e = threadIdx.x; e < dd; e += 256) {
-        const double v = (double)src[e];
-        acc += v * v;
+    for (long long b = blockIdx.y; b < batch; b += gridDim.y) {        // grid.y is capped at 65535
+        const T* __restrict__ src = F + lo * batch + b * dd;
+        double acc = 0.0;
+        for (long long e = threadIdx.x; e < dd; e += 256) {
+            const double v = (double)src[e];
+            acc += v * v;
+        }
+        const double tot = block_sum_256(acc, part);
+        if (threadIdx.x == 0) out[(long long)lam * batch + b] = (T)(tot * (double)dims[lam] * inv_order);
     }
-    part[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[(long long)lam * batch + b] = (T)(part[0] * (double)dims[lam] * inv_order);
 }
 
 // ---------------------------------------------------------------------------

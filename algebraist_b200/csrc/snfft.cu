@@ -39,7 +39,6 @@
 #include <vector>
 
 #include "kernels.cuh"
-#include "level_tb.cuh"
 #include "plan.h"
 
 namespace snfft {
@@ -75,7 +74,7 @@ static const int kNumClasses = 6;
 static std::atomic<int> g_force_class{-1};
 static std::atomic<int> g_no_base{0};
 static std::atomic<int> g_no_vec_gather{0};   // test hook: 1 = always the scalar gather / scatter kernel
-static std::atomic<int> g_tb_mode{-1};      // -1 automatic, 0 sweep-per-pass kernels only, 1..3 force s fused top sweeps
+static std::atomic<int> g_tb_mode{-1};      // -1 automatic kernel choice, >= 0 table-driven sweep kernels at every level >= 6 (cross-check)
 static std::atomic<long long> g_launches{0};
 static thread_local std::string g_error;
 
@@ -126,26 +125,18 @@ struct TaskRange {
     long long elems;      // coefficients this launch produces per instance (its share of k!)
 };
 
-struct TbRange {          // one launch of the TB kernels: tasks that share a tile width
-    int tcl, nt, begin, count, max_dmu, max_dlam, max_tt, max_ct, max_bt, max_nsb;
-    long long elems;
-};
-
 struct DevLevel {
     // column kernels (col_kernels.cuh, levels 6..8): registers only; chosen when the plan is created
     bool col_fwd = false, col_inv = false;
     // top / bottom kernels (tz_kernels.cuh, levels 9 and 10): two streaming launches per step through the third
     // workspace buffer; chosen when the plan is created
     bool tz_fwd = false, tz_inv = false;
-    // TB kernels (level_tb.cuh): tb_s = 0 means the level runs the sweep-per-pass kernels
-    int tb_s = 0;
-    int tb_inv_nbuf = 2;                      // chains per pass of the inverse TB kernel at this level
-    bool tb_fwd = false, tb_inv = false;      // which directions use them (the other runs the sweep kernels)
-    void *tb_tasks = nullptr, *tb_itasks = nullptr, *tb_tt = nullptr, *tb_ct = nullptr, *tb_bt = nullptr;
-    std::vector<TbRange> tb_franges, tb_iranges;
     void* tables = nullptr;
     void *ftasks = nullptr, *itasks = nullptr, *parents = nullptr;
     int nftasks = 0, nitasks = 0, tab_words = 0;
+    std::vector<FwdTask> h_ftasks;            // host copies (snfft_subplan_create filters them)
+    std::vector<InvTask> h_itasks;
+    std::vector<InvParent> h_parents;
     double lut_a[LUT], lut_b[LUT];
     std::vector<TaskRange> franges, iranges;
 };
@@ -182,6 +173,23 @@ struct snfft_plan {
     // scratch of the *_host entry points
     void *h_in = nullptr, *h_out = nullptr, *h_ws = nullptr;
     size_t h_io_bytes = 0, h_ws_bytes = 0;
+};
+
+// A subset of the partitions of n and what the pruned pipeline needs to compute only those (SURVEY 8f.4:
+// band-limited transforms): the level steps k >= k_first run the table-driven sweep kernels on task lists
+// filtered to the down-closure of the subset in Young's lattice (a block of F_lambda only needs the blocks of the
+// shapes contained in lambda, fourier.py:259-265); the levels below run the plan's ordinary kernels.
+struct SubLevel {
+    void *ftasks = nullptr, *itasks = nullptr, *parents = nullptr;
+    std::vector<snfft::TaskRange> franges, iranges;
+};
+struct snfft_subplan {
+    const snfft_plan* plan = nullptr;
+    int k_first = 0;                          // first pruned level (n + 1: nothing is pruned)
+    std::vector<std::vector<char>> keep;      // keep[k][shape]
+    std::vector<SubLevel> lev;
+    std::vector<void*> allocs;
+    double kept_fraction = 1.0;               // sum of d^2 over the kept partitions of n / n!
 };
 
 namespace snfft {
@@ -355,6 +363,9 @@ static int build_level(snfft_plan* p, int k) {
     D.nftasks = (int)ftasks.size();
     D.nitasks = (int)itasks.size();
     D.tab_words = (int)tables.size();
+    D.h_ftasks = ftasks;
+    D.h_itasks = itasks;
+    D.h_parents = parents;
     int rc;
     if ((rc = upload(p, tables, &D.tables))) return rc;
     if ((rc = upload(p, ftasks, &D.ftasks))) return rc;
@@ -401,7 +412,19 @@ static int set_smem(KF kfn, size_t bytes) {
     return SNFFT_OK;
 }
 
-#include "tb_host.inl"
+// Tuning / test switches: environment variables that list levels ("7,8,9"; "" = none), read when a plan is created.
+static bool level_listed(const char* env, int k, bool dflt) {
+    const char* e = std::getenv(env);
+    if (!e) return dflt;
+    for (const char* q = e; *q;) {
+        char* end;
+        const long v = std::strtol(q, &end, 10);
+        if (end == q) break;
+        if (v == k) return true;
+        q = (*end == ',') ? end + 1 : end;
+    }
+    return false;
+}
 
 template <typename T, int V, int W, int G, int RPT, int NG, int NBUF, int MINB, bool STAGE>
 static int launch_fwd_range(const TaskRange& r, LevelArgs<T> a, cudaStream_t st) {
@@ -468,15 +491,18 @@ static LevelArgs<T> level_args(const snfft_plan* p, int k, const void* in, void*
 }
 
 // nch > 0: only the cosets cid[0..nch) (ascending) are present in `in` (nch planes per coefficient)
+// `sub_tasks` / `sub_ranges`: a filtered task list of the same level (snfft_subplan), else the plan's own
 template <typename T>
 static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st,
-                         int nch = 0, const int* cid = nullptr) {
+                         int nch = 0, const int* cid = nullptr, const void* sub_tasks = nullptr,
+                         const std::vector<TaskRange>* sub_ranges = nullptr) {
     LevelArgs<T> a = level_args<T>(p, k, in, out, B);
     if (nch > 0) {
         a.nch = nch;
         for (int j = 0; j < nch; ++j) a.cid[j] = cid[j];
     }
-    for (const TaskRange& r : p->lev[k].franges) {
+    if (sub_ranges) a.ftasks = (const FwdTask*)sub_tasks;
+    for (const TaskRange& r : (sub_ranges ? *sub_ranges : p->lev[k].franges)) {
         int rc = SNFFT_ENOTSUP;
         ProfScope prof(p, st, 0, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
@@ -495,9 +521,15 @@ static int run_fwd_level(const snfft_plan* p, int k, const void* in, void* out, 
 }
 
 template <typename T>
-static int run_inv_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st) {
-    const LevelArgs<T> a = level_args<T>(p, k, in, out, B);
-    for (const TaskRange& r : p->lev[k].iranges) {
+static int run_inv_level(const snfft_plan* p, int k, const void* in, void* out, long long B, cudaStream_t st,
+                         const void* sub_tasks = nullptr, const void* sub_parents = nullptr,
+                         const std::vector<TaskRange>* sub_ranges = nullptr) {
+    LevelArgs<T> a = level_args<T>(p, k, in, out, B);
+    if (sub_ranges) {
+        a.itasks = (const InvTask*)sub_tasks;
+        a.parents = (const InvParent*)sub_parents;
+    }
+    for (const TaskRange& r : (sub_ranges ? *sub_ranges : p->lev[k].iranges)) {
         int rc = SNFFT_ENOTSUP;
         ProfScope prof(p, st, 1, k, r.cls, r.elems);
         if constexpr (sizeof(T) == 4) {
@@ -541,54 +573,11 @@ static int run_gather(const snfft_plan* p, const void* in, void* out, long long 
         SNFFT_CUDA(cudaGetLastError());
         return SNFFT_OK;
     }
-    dim3 grid((unsigned)((ia.nfact + GS_TR - 1) / GS_TR), (unsigned)((B + GS_TB - 1) / GS_TB), 1);
+    dim3 grid((unsigned)((ia.nfact + GS_TR - 1) / GS_TR), (unsigned)std::min<long long>((B + GS_TB - 1) / GS_TB, 65535), 1);
     dim3 block(GS_THREADS, 1, 1);
     ProfScope prof(p, st, SCATTER ? 3 : 2, 1, -1, ia.nfact);
     auto kfn = gather_kernel<T, SCATTER>;
     SNFFT_LAUNCH(kfn, grid, block, gather_smem_bytes<T>(), st, (const T*)in, (T*)out, ia);
-    g_launches.fetch_add(1);
-    SNFFT_CUDA(cudaGetLastError());
-    return SNFFT_OK;
-}
-
-// Fused levels 2..K0 (forward) or K0..2 (inverse) on level-K0 instance tiles.
-static const int kBaseK0 = 6;
-
-template <typename T, bool INVERSE>
-static int run_base(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
-    constexpr int TI = sizeof(T) == 4 ? 32 : 16, NW = 16, DMAXB = 16;
-    BaseArgs<T> a;
-    a.in = (const T*)in;
-    a.out = (T*)out;
-    a.k0 = kBaseK0;
-    a.ninst = B * (p->host.factorial[p->n] / p->host.factorial[kBaseK0]);
-    a.tab_smem_words = 0;
-    for (int k = 0; k <= BASE_MAXK; ++k) a.fact[k] = p->host.factorial[k];
-    for (int k = 2; k <= kBaseK0; ++k) {
-        const DevLevel& D = p->lev[k];
-        if (p->host.levels[k].max_dim > DMAXB) return set_error(SNFFT_ENOTSUP, "base kernel: irrep too large");
-        BaseLevel<T>& L = a.lev[k];
-        L.ftasks = (const FwdTask*)D.ftasks;
-        L.itasks = (const InvTask*)D.itasks;
-        L.parents = (const InvParent*)D.parents;
-        L.tables = (const uint32_t*)D.tables;
-        L.nftasks = D.nftasks;
-        L.nitasks = D.nitasks;
-        L.tab_words = D.tab_words;
-        L.pad = 0;
-        for (int c = 0; c < LUT; ++c) {
-            L.lut[c] = (T)D.lut_a[c];
-            L.lut[LUT + c] = (T)D.lut_b[c];
-        }
-        a.tab_smem_words = std::max(a.tab_smem_words, D.tab_words);
-    }
-    const size_t smem = base_smem_bytes<T, TI, NW, DMAXB>((int)p->host.factorial[kBaseK0], a.tab_smem_words);
-    dim3 grid((unsigned)((a.ninst + TI - 1) / TI), 1, 1), block(NW * 32, 1, 1);
-    ProfScope prof(p, st, INVERSE ? 5 : 4, kBaseK0, -1, p->host.factorial[kBaseK0]);
-    auto kfn = base_kernel<T, TI, NW, DMAXB, INVERSE>;
-    int rc;
-    if ((rc = set_smem(kfn, smem))) return rc;
-    SNFFT_LAUNCH(kfn, grid, block, smem, st, a);
     g_launches.fetch_add(1);
     SNFFT_CUDA(cudaGetLastError());
     return SNFFT_OK;
@@ -627,25 +616,13 @@ static int run_pack(const snfft_plan* p, const void* in, void* out, long long B,
     return SNFFT_OK;
 }
 
-// Generated register kernels: levels 2..5 of every S_5 instance, and level 6.
+// Generated register kernel: levels 2..5 of every S_5 instance.
 template <typename T, bool INVERSE>
 static int run_s5(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
     const long long ninst = B * (p->host.factorial[p->n] / 120);
     dim3 grid((unsigned)((ninst + GEN_THREADS - 1) / GEN_THREADS), 1, 1), block(GEN_THREADS, 1, 1);
     ProfScope prof(p, st, INVERSE ? 5 : 4, 5, -1, 120);
     auto kfn = s5_kernel<T, INVERSE>;
-    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)in, (T*)out, ninst);
-    g_launches.fetch_add(1);
-    SNFFT_CUDA(cudaGetLastError());
-    return SNFFT_OK;
-}
-
-template <typename T, bool INVERSE>
-static int run_l6(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
-    const long long ninst = B * (p->host.factorial[p->n] / 720);
-    dim3 grid((unsigned)((ninst + GEN_THREADS - 1) / GEN_THREADS), 1, 1), block(GEN_THREADS, 1, 1);
-    ProfScope prof(p, st, INVERSE ? 5 : 4, 6, -1, 720);
-    auto kfn = l6_kernel<T, INVERSE>;
     SNFFT_LAUNCH(kfn, grid, block, 0, st, (const T*)in, (T*)out, ninst);
     g_launches.fetch_add(1);
     SNFFT_CUDA(cudaGetLastError());
@@ -669,12 +646,12 @@ SNFFT_COL9_DECL(0) SNFFT_COL9_DECL(1) SNFFT_COL9_DECL(2) SNFFT_COL9_DECL(3)
 constexpr int kColFirst = 6, kColLast = 9, kColLastInv = 8;      // level 9: forward only, four launches
 
 // Levels that use the column kernels: automatic kernel choice only (the forced TB / sweep modes of
-// snfft_debug_tb_mode keep testing those families), SNFFT_COL_FWD / SNFFT_COL_INV (lists of levels) override.
+// snfft_debug_tb_mode keep testing the sweep kernels), SNFFT_COL_FWD / SNFFT_COL_INV (lists of levels) override.
 static void col_pick_dirs(int k, bool* fwd, bool* inv) {
     *fwd = *inv = false;
     if (k < kColFirst || k > kColLast || g_tb_mode.load() != -1) return;
-    *fwd = tb_level_listed("SNFFT_COL_FWD", k, true);
-    *inv = k <= kColLastInv && tb_level_listed("SNFFT_COL_INV", k, true);
+    *fwd = level_listed("SNFFT_COL_FWD", k, true);
+    *inv = k <= kColLastInv && level_listed("SNFFT_COL_INV", k, true);
 }
 
 template <typename T, bool INVERSE>
@@ -726,8 +703,8 @@ static int tz_mb(int k) { return k == 11 ? 8 : 7; }       // gen_tz.py LEVEL_MB
 static void tz_pick_dirs(int k, bool* fwd, bool* inv) {
     *fwd = *inv = false;
     if (k < kTzFirst || k > kTzLast || g_tb_mode.load() != -1) return;
-    *fwd = tb_level_listed("SNFFT_TZ_FWD", k, true);
-    *inv = tb_level_listed("SNFFT_TZ_INV", k, true);
+    *fwd = level_listed("SNFFT_TZ_FWD", k, true);
+    *inv = level_listed("SNFFT_TZ_INV", k, true);
 }
 
 static int tz_prepare(int dtype, int k, bool fwd, bool inv) {
@@ -795,13 +772,14 @@ static IndexArgs make_index_args(int n);
 
 // level steps k_first .. n of the forward pipeline: cur = X_{k_first - 1} on entry, X_n on return
 template <typename T>
-static int forward_level_range(const snfft_plan* p, int k_first, void*& cur, void*& nxt, void* zbuf, long long B, cudaStream_t st) {
+static int forward_level_range(const snfft_plan* p, int k_first, void*& cur, void*& nxt, void* zbuf, long long B, cudaStream_t st,
+                               int k_stop = -1) {
     const int base = g_no_base.load();
-    for (int k = k_first; k <= p->n; ++k) {
+    const int k_end = k_stop < 0 ? p->n : k_stop - 1;
+    for (int k = k_first; k <= k_end; ++k) {
         int rc;
         if (base == 0 && p->lev[k].tz_fwd) rc = run_tz_level<T, false>(p, k, cur, nxt, zbuf, B, st);
         else if (base == 0 && p->lev[k].col_fwd) rc = run_col_level<T, false>(p, k, cur, nxt, B, st);
-        else if (p->lev[k].tb_s > 0 && p->lev[k].tb_fwd) rc = run_tb_level<T, false>(p, k, cur, nxt, B, st);
         else rc = run_fwd_level<T>(p, k, cur, nxt, B, st);
         if (rc) return rc;
         std::swap(cur, nxt);
@@ -811,7 +789,8 @@ static int forward_level_range(const snfft_plan* p, int k_first, void*& cur, voi
 
 // levels 1..n of the forward pipeline; *result points at X_n (instance fastest) inside the workspace
 template <typename T>
-static int forward_levels(const snfft_plan* p, const void* f, long long B, void* ws, cudaStream_t st, void** result) {
+static int forward_levels(const snfft_plan* p, const void* f, long long B, void* ws, cudaStream_t st, void** result,
+                          int k_stop = -1, void** other = nullptr) {          // k_stop: stop before that level step
     const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
     void* cur = ws;
     void* nxt = (char*)ws + half;
@@ -819,23 +798,15 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
     int rc;
     if ((rc = run_gather<T, false>(p, f, cur, B, st))) return rc;
     int k_first = 2;
-    const int base = g_no_base.load();          // 0: generated register kernels, 1: level kernels, 2: shared-memory base kernel
+    const int base = g_no_base.load();          // 0: generated register kernels for levels 2..5, else table-driven level kernels
     if (base == 0 && p->n > 5) {
         if ((rc = run_s5<T, false>(p, cur, nxt, B, st))) return rc;
         std::swap(cur, nxt);
         k_first = 6;
-        if (p->n > 6) {
-            if ((rc = p->lev[6].col_fwd ? run_col_level<T, false>(p, 6, cur, nxt, B, st) : run_l6<T, false>(p, cur, nxt, B, st))) return rc;
-            std::swap(cur, nxt);
-            k_first = 7;
-        }
-    } else if (base == 2 && p->n > kBaseK0) {
-        if ((rc = run_base<T, false>(p, cur, nxt, B, st))) return rc;
-        std::swap(cur, nxt);
-        k_first = kBaseK0 + 1;
     }
-    if ((rc = forward_level_range<T>(p, k_first, cur, nxt, zbuf, B, st))) return rc;
+    if ((rc = forward_level_range<T>(p, k_first, cur, nxt, zbuf, B, st, k_stop))) return rc;
     *result = cur;
+    if (other) *other = nxt;
     return SNFFT_OK;
 }
 
@@ -939,41 +910,81 @@ static int forward_cosets2_impl(const snfft_plan* pn, const snfft_plan* pm, cons
 }
 
 template <typename T>
+static int inverse_tail(const snfft_plan* p, int k_top, const void* cur, void** bufs, int which, void* zbuf, long long B,
+                        void* f, cudaStream_t st);
+
+template <typename T>
 static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f, void* ws, cudaStream_t st) {
     const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
     void* bufs[2] = {ws, (char*)ws + half};
     void* zbuf = (char*)ws + 2 * half;
-    int which = 1, rc;
+    int rc;
     if ((rc = run_pack<T, false>(p, F, bufs[0], B, st))) return rc;
-    const void* cur = bufs[0];
+    return inverse_tail<T>(p, p->n, bufs[0], bufs, 1, zbuf, B, f, st);
+}
+
+// level steps k_top .. 2 of the inverse pipeline and the final scatter: cur = X_{k_top} on entry
+template <typename T>
+static int inverse_tail(const snfft_plan* p, int k_top, const void* cur, void** bufs, int which, void* zbuf, long long B,
+                        void* f, cudaStream_t st) {
+    int rc;
     const int base = g_no_base.load();
-    int k_last = 2;                             // lowest level the per-level kernels handle
-    if (base == 0 && p->n > 5) k_last = p->n > 6 ? 7 : 6;
-    else if (base == 2 && p->n > kBaseK0) k_last = kBaseK0 + 1;
-    for (int k = p->n; k >= k_last; --k) {
+    const int k_last = (base == 0 && p->n > 5) ? 6 : 2;      // lowest level the per-level kernels handle
+    for (int k = k_top; k >= k_last; --k) {
         if (base == 0 && p->lev[k].tz_inv) rc = run_tz_level<T, true>(p, k, cur, bufs[which], zbuf, B, st);
         else if (base == 0 && p->lev[k].col_inv) rc = run_col_level<T, true>(p, k, cur, bufs[which], B, st);
-        else if (p->lev[k].tb_s > 0 && p->lev[k].tb_inv) rc = run_tb_level<T, true>(p, k, cur, bufs[which], B, st);
         else rc = run_inv_level<T>(p, k, cur, bufs[which], B, st);
         if (rc) return rc;
         cur = bufs[which];
         which ^= 1;
     }
     if (base == 0 && p->n > 5) {
-        if (p->n > 6) {
-            if ((rc = p->lev[6].col_inv ? run_col_level<T, true>(p, 6, cur, bufs[which], B, st) : run_l6<T, true>(p, cur, bufs[which], B, st))) return rc;
-            cur = bufs[which];
-            which ^= 1;
-        }
         if ((rc = run_s5<T, true>(p, cur, bufs[which], B, st))) return rc;
-        cur = bufs[which];
-        which ^= 1;
-    } else if (base == 2 && p->n > kBaseK0) {
-        if ((rc = run_base<T, true>(p, cur, bufs[which], B, st))) return rc;
         cur = bufs[which];
         which ^= 1;
     }
     return run_gather<T, true>(p, cur, f, B, st);
+}
+
+constexpr int kSubFirst = 8;        // lowest level the subset transforms prune (levels below run the column kernels)
+
+template <typename T>
+static int forward_subset_impl(const snfft_plan* p, const snfft_subplan* sp, const void* f, long long B, void* F, void* ws,
+                               cudaStream_t st) {
+    if (sp->k_first > p->n || g_no_base.load() != 0) return forward_impl<T>(p, f, B, F, ws, st);
+    const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
+    void *cur = nullptr, *nxt = nullptr;
+    int rc = forward_levels<T>(p, f, B, ws, st, &cur, sp->k_first, &nxt);
+    if (rc) return rc;
+    for (int k = sp->k_first; k <= p->n; ++k) {
+        // the partitions outside the subset come out as zeros
+        if (k == p->n) SNFFT_CUDA(cudaMemsetAsync(nxt, 0, half, st));
+        const SubLevel& L = sp->lev[k];
+        if ((rc = run_fwd_level<T>(p, k, cur, nxt, B, st, 0, nullptr, L.ftasks, &L.franges))) return rc;
+        std::swap(cur, nxt);
+    }
+    return run_pack<T, true>(p, cur, F, B, st);
+}
+
+template <typename T>
+static int inverse_subset_impl(const snfft_plan* p, const snfft_subplan* sp, const void* F, long long B, void* f, void* ws,
+                               cudaStream_t st) {
+    if (sp->k_first > p->n || g_no_base.load() != 0) return inverse_impl<T>(p, F, B, f, ws, st);
+    const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
+    void* bufs[2] = {ws, (char*)ws + half};
+    void* zbuf = (char*)ws + 2 * half;
+    int which = 1, rc;
+    if ((rc = run_pack<T, false>(p, F, bufs[0], B, st))) return rc;
+    const void* cur = bufs[0];
+    for (int k = p->n; k >= sp->k_first; --k) {
+        // the level below the last pruned step runs the ordinary kernels: it must see zeros outside the subset
+        if (k == sp->k_first) SNFFT_CUDA(cudaMemsetAsync(bufs[which], 0, half, st));
+        const SubLevel& L = sp->lev[k];
+        if ((rc = run_inv_level<T>(p, k, cur, bufs[which], B, st, L.itasks, L.parents, &L.iranges))) return rc;
+        cur = bufs[which];
+        which ^= 1;
+    }
+    return inverse_tail<T>(p, sp->k_first - 1, cur, bufs, which, zbuf, B, f, st);
 }
 
 static IndexArgs make_index_args(int n) {
@@ -1091,8 +1102,8 @@ int64_t snfft_launch_count(void) { return (int64_t)g_launches.load(); }
 // affects plans created afterwards.
 void snfft_debug_force_class(int cls) { g_force_class.store(cls); }
 
-// test hook: how levels 2..6 run.  0 = generated register kernels (default), 1 = per-level
-// table-driven kernels, 2 = table-driven shared-memory base kernel
+// test hook: how the levels run.  0 = generated kernels (default), != 0 = the table-driven sweep kernels at EVERY
+// level (second implementation, used as a cross-check)
 void snfft_debug_disable_base(int mode) { g_no_base.store(mode); }
 void snfft_debug_tb_mode(int mode) { g_tb_mode.store(mode); }
 void snfft_debug_scalar_gather(int on) { g_no_vec_gather.store(on); }
@@ -1165,17 +1176,6 @@ int snfft_plan_create(int n, int dtype, int device, snfft_plan_t** out) {
             col_pick_dirs(k, &p->lev[k].col_fwd, &p->lev[k].col_inv);
             tz_pick_dirs(k, &p->lev[k].tz_fwd, &p->lev[k].tz_inv);
             if (!rc) rc = tz_prepare(dtype, k, p->lev[k].tz_fwd, p->lev[k].tz_inv);
-            const int s = tb_pick_s(k);
-            if (!rc && s > 0 && k - s >= 3) {
-                rc = dtype == SNFFT_F32 ? build_tb_level<float>(p, k, s) : build_tb_level<double>(p, k, s);
-                tb_pick_dirs(k, dtype, &p->lev[k].tb_fwd, &p->lev[k].tb_inv);
-                if (rc == SNFFT_ENOTSUP) {          // shapes too large for the TB tiles: keep the sweep kernels
-                    p->lev[k].tb_s = 0;
-                    p->lev[k].tb_franges.clear();
-                    p->lev[k].tb_iranges.clear();
-                    rc = SNFFT_OK;
-                }
-            }
             if (rc) {
                 snfft_plan_destroy(p);
                 return rc;
@@ -1329,6 +1329,156 @@ int snfft_forward_cosets2(const snfft_plan_t* pn, const snfft_plan_t* pm, const 
                                   : forward_cosets2_impl<double>(pn, pm, f, B, top, sub, npairs, F, ws, st);
 }
 
+extern "C++" {
+template <typename V>
+static int sub_upload(snfft_subplan* sp, const std::vector<V>& v, void** out) {
+    *out = nullptr;
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(v.size() * sizeof(V), 16)) != cudaSuccess)
+        return set_error(SNFFT_ENOMEM, "cudaMalloc of subset-plan table failed");
+    sp->allocs.push_back(d);
+    if (!v.empty()) SNFFT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+    *out = d;
+    return SNFFT_OK;
+}
+}  // extern "C++"
+
+int snfft_subplan_create(const snfft_plan_t* p, const int32_t* keep, snfft_subplan_t** out) {
+    if (!p || !keep || !out) return set_error(SNFFT_EINVAL, "NULL plan, mask or output");
+    *out = nullptr;
+    const int n = p->n;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return set_error(SNFFT_ECUDA, "cudaSetDevice failed");
+    snfft_subplan* sp = new (std::nothrow) snfft_subplan();
+    if (!sp) return set_error(SNFFT_ENOMEM, "out of host memory");
+    sp->plan = p;
+    sp->keep.resize(n + 1);
+    sp->lev.resize(n + 1);
+    const HostLevel& Ln = p->host.levels[n];
+    sp->keep[n].assign(Ln.shapes.size(), 0);
+    double kept = 0.0;
+    bool any = false;
+    for (size_t q = 0; q < Ln.shapes.size(); ++q)
+        if (keep[q]) {
+            sp->keep[n][q] = 1;
+            kept += (double)Ln.shapes[q].dim * Ln.shapes[q].dim;
+            any = true;
+        }
+    if (!any) {
+        delete sp;
+        return set_error(SNFFT_EINVAL, "the subset of partitions is empty");
+    }
+    sp->kept_fraction = kept / (double)p->host.factorial[n];
+    sp->k_first = n >= kSubFirst ? kSubFirst : n + 1;
+    for (int k = n; k >= sp->k_first; --k) {           // down-closure: the children of every kept shape
+        const HostLevel& L = p->host.levels[k];
+        sp->keep[k - 1].assign(p->host.levels[k - 1].shapes.size(), 0);
+        for (size_t q = 0; q < L.shapes.size(); ++q)
+            if (sp->keep[k][q])
+                for (int c : L.shapes[q].child) sp->keep[k - 1][c] = 1;
+    }
+    int rc = SNFFT_OK;
+    for (int k = sp->k_first; k <= n && !rc; ++k) {
+        const HostLevel& L = p->host.levels[k];
+        const HostLevel& P = p->host.levels[k - 1];
+        const DevLevel& D = p->lev[k];
+        auto shape_of = [](const HostLevel& H, long long coef_off) {
+            for (size_t q = 0; q < H.shapes.size(); ++q)
+                if (H.shapes[q].coef_off == coef_off) return (int)q;
+            return -1;
+        };
+        SubLevel& S = sp->lev[k];
+        std::vector<FwdTask> ft;
+        for (const TaskRange& r : D.franges) {
+            TaskRange nr{r.cls, (int)ft.size(), 0, 0, 0, 0, 0};
+            for (int t = r.begin; t < r.begin + r.count; ++t) {
+                const FwdTask& task = D.h_ftasks[t];
+                const int q = shape_of(L, task.lam_off);
+                if (q < 0 || !sp->keep[k][q]) continue;
+                ft.push_back(task);
+                nr.count += 1;
+                nr.elems += (long long)task.d_lam * task.d_mu;
+                nr.max_tab = std::max(nr.max_tab, task.tab_words);
+                nr.max_dmu = std::max(nr.max_dmu, task.d_mu);
+                nr.max_dlam = std::max(nr.max_dlam, task.d_lam);
+            }
+            if (nr.count) S.franges.push_back(nr);
+        }
+        std::vector<InvTask> it;
+        std::vector<InvParent> par;
+        for (const TaskRange& r : D.iranges) {
+            TaskRange nr{r.cls, (int)it.size(), 0, 0, 0, 0, 0};
+            for (int t = r.begin; t < r.begin + r.count; ++t) {
+                InvTask task = D.h_itasks[t];
+                const int m = shape_of(P, task.mu_off);
+                if (m < 0 || !sp->keep[k - 1][m]) continue;
+                const int par0 = (int)par.size();
+                int maxd = 0, maxtab = 0;
+                for (int q = task.par_off; q < task.par_off + task.npar; ++q) {
+                    const InvParent& ip = D.h_parents[q];
+                    const int lam = shape_of(L, ip.lam_off);
+                    if (lam < 0 || !sp->keep[k][lam]) continue;
+                    par.push_back(ip);
+                    maxd = std::max(maxd, ip.d_lam);
+                    maxtab = std::max(maxtab, ip.tab_words);
+                }
+                task.par_off = par0;
+                task.npar = (int)par.size() - par0;
+                if (task.npar == 0) continue;             // cannot happen: mu is the child of a kept shape
+                it.push_back(task);
+                nr.count += 1;
+                nr.elems += (long long)k * task.d_mu * task.d_mu;
+                nr.max_tab = std::max(nr.max_tab, maxtab);
+                nr.max_dmu = std::max(nr.max_dmu, task.d_mu);
+                nr.max_dlam = std::max(nr.max_dlam, maxd);
+            }
+            if (nr.count) S.iranges.push_back(nr);
+        }
+        if (!rc) rc = sub_upload(sp, ft, &S.ftasks);
+        if (!rc) rc = sub_upload(sp, it, &S.itasks);
+        if (!rc) rc = sub_upload(sp, par, &S.parents);
+    }
+    if (rc) {
+        snfft_subplan_destroy(sp);
+        return rc;
+    }
+    *out = sp;
+    return SNFFT_OK;
+}
+
+void snfft_subplan_destroy(snfft_subplan_t* sp) {
+    if (!sp) return;
+    for (void* d : sp->allocs) cudaFree(d);
+    delete sp;
+}
+
+int snfft_subplan_info(const snfft_subplan_t* sp, int* first_pruned_level, double* kept_fraction) {
+    if (!sp) return set_error(SNFFT_EINVAL, "subset plan is NULL");
+    if (first_pruned_level) *first_pruned_level = sp->k_first;
+    if (kept_fraction) *kept_fraction = sp->kept_fraction;
+    return SNFFT_OK;
+}
+
+int snfft_forward_subset(const snfft_plan_t* p, const snfft_subplan_t* sp, const void* f, int64_t B, void* F, void* ws,
+                         size_t ws_bytes, void* stream) {
+    int rc = check_io(p, f, F, B, ws, ws_bytes);
+    if (rc || B == 0) return rc;
+    if (!sp || sp->plan != p) return set_error(SNFFT_EINVAL, "the subset plan does not belong to this plan");
+    cudaStream_t st = (cudaStream_t)stream;
+    return p->dtype == SNFFT_F32 ? forward_subset_impl<float>(p, sp, f, B, F, ws, st)
+                                 : forward_subset_impl<double>(p, sp, f, B, F, ws, st);
+}
+
+int snfft_inverse_subset(const snfft_plan_t* p, const snfft_subplan_t* sp, const void* F, int64_t B, void* f, void* ws,
+                         size_t ws_bytes, void* stream) {
+    int rc = check_io(p, F, f, B, ws, ws_bytes);
+    if (rc || B == 0) return rc;
+    if (!sp || sp->plan != p) return set_error(SNFFT_EINVAL, "the subset plan does not belong to this plan");
+    cudaStream_t st = (cudaStream_t)stream;
+    return p->dtype == SNFFT_F32 ? inverse_subset_impl<float>(p, sp, F, B, f, ws, st)
+                                 : inverse_subset_impl<double>(p, sp, F, B, f, ws, st);
+}
+
 int snfft_block_matmul(const snfft_plan_t* p, const void* A, const void* Bm, void* C, int64_t B, void* stream) {
     if (!p) return set_error(SNFFT_EINVAL, "plan is NULL");
     if (B < 0) return set_error(SNFFT_EINVAL, "negative batch");
@@ -1361,9 +1511,8 @@ int snfft_power(const snfft_plan_t* p, const void* F, int64_t B, void* out, void
     if (B < 0) return set_error(SNFFT_EINVAL, "negative batch");
     if (B == 0) return SNFFT_OK;
     if (!F || !out) return set_error(SNFFT_EINVAL, "NULL data pointer");
-    if (B > 65535) return set_error(SNFFT_ENOTSUP, "snfft_power: batch above 65535");
     const HostLevel& L = p->host.levels[p->n];
-    dim3 grid((unsigned)L.shapes.size(), (unsigned)B, 1), block(256, 1, 1);
+    dim3 grid((unsigned)L.shapes.size(), (unsigned)std::min<int64_t>(B, 65535), 1), block(256, 1, 1);
     const double inv_order = 1.0 / (double)p->host.factorial[p->n];
     cudaStream_t st = (cudaStream_t)stream;
     if (p->dtype == SNFFT_F32) {

@@ -23,6 +23,16 @@ def shard_bounds(batch: int, world_size: int, rank: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def _irrep_dim(lam) -> int:
+    """Hook-length formula (tableau.py:236-265)."""
+    n = sum(lam)
+    prod = 1
+    for i, row in enumerate(lam):
+        for j in range(row):
+            prod *= row - j + sum(1 for r in lam[i + 1:] if r > j)
+    return math.factorial(n) // prod
+
+
 def sn_fft_batch_sharded(fn_vals: torch.Tensor, n: int, group=None, gather: bool = False) -> dict:
     """Forward transform of the rows this rank owns of a (B, n!) tensor that every
     rank holds (or of a local shard if `fn_vals` is already the local rows: pass
@@ -41,7 +51,7 @@ def sn_fft_batch_sharded(fn_vals: torch.Tensor, n: int, group=None, gather: bool
     spans = [shard_bounds(full, world, r) for r in range(world)]
     longest = max(b - a for a, b in spans)
     for lam, v in local.items():
-        d = 1 if v.numel() == hi - lo else int(round(math.sqrt(v.numel() // max(hi - lo, 1))))
+        d = _irrep_dim(lam)         # from the partition (a rank that owns no rows cannot infer it from its tensor)
         # n <= 5 squeezes a single local row (fourier.py:129): restore the batch axis before gathering
         v = v.reshape((hi - lo,) + ((d, d) if d > 1 else ()))
         # all_gather wants equal shapes: pad the short shards with zero rows, trim afterwards

@@ -225,23 +225,163 @@ def sn_ifft(ft: dict, n: int) -> torch.Tensor:
     return out if home == out.device else out.to(home)
 
 
+# The pruned level steps run the table-driven sweep kernels, which are several times slower per coefficient than
+# the generated kernels of the full pipeline: the subset path wins while the kept partitions hold less than
+# about 3 % of the coefficients (S_10 fp32, batch 128: k = 1, 2, 3 -> 3.7 / 3.9 / 5.0 ms against 7.6 ms for the
+# full forward transform, k = 4 with 9 % of the coefficients 8.7 ms; profiles r02j).
+_SUBSET_MAX_FRACTION = 0.03
+
+
+def _inverse_subset_packed(plan, sub, packed: torch.Tensor, batch: int) -> torch.Tensor:
+    """Inverse of a packed coefficient array that is zero outside the subset plan's partitions."""
+    if plan.subplan_info(sub)[1] > _SUBSET_MAX_FRACTION:
+        return _inverse_packed(plan, packed, batch)
+    out = torch.empty((batch, plan.nfact), dtype=packed.dtype, device=packed.device)
+    if batch:
+        with _device_ctx(packed.device):
+            ws = plan.workspace(batch)
+            _lib.check(_lib.load().snfft_inverse_subset(plan.handle, sub, packed.data_ptr(), batch, out.data_ptr(),
+                                                        ws.data_ptr(), ws.numel(), _stream_ptr(packed.device)),
+                       "snfft_inverse_subset")
+    return out
+
+
 def sn_fourier_decomposition(ft: dict, n: int) -> dict:
     """Per-partition components of the inverse transform (reference fourier.py:291-295):
     {lambda: d_lambda/n! <F(lambda), rho_lambda(.)>}, whose sum over lambda is sn_ifft(ft, n).
-    Each component is the inverse pipeline run on the coefficients of one partition with every other
-    block zero (the reference's own recursion raises for n > 5, fourier.py:202-214)."""
+    Each component is the inverse pipeline restricted to one partition (`snfft_inverse_subset`: the level steps
+    k >= 8 only touch the shapes contained in lambda); the reference's own recursion raises for n > 5
+    (fourier.py:202-214)."""
     plan, packed, batch, lead, home = _pack_ft(ft, n)
     one = torch.zeros_like(packed)
     out = {}
-    for lam, d, off in zip(plan.partitions, plan.dims, plan.offsets):
+    for p, (lam, d, off) in enumerate(zip(plan.partitions, plan.dims, plan.offsets)):
         blk = slice(off * batch, (off + d * d) * batch)
         one[blk].copy_(packed[blk])
-        comp = _inverse_packed(plan, one, batch).view(lead + (plan.nfact,))
+        comp = _inverse_subset_packed(plan, plan.subplan([p]), one, batch).view(lead + (plan.nfact,))
         one[blk].zero_()
         if n <= BASE_CASE:
             comp = comp.squeeze()
         out[lam] = comp if home == comp.device else comp.to(home)
     return out
+
+
+def bandlimited_partitions(n: int, k: int):
+    """The partitions of n with lambda_1 >= n - k, in generate_partitions order: the "low-frequency" irreps of
+    ranking / partial-ranking analyses (k = 1: the trivial and the (n-1, 1) irrep).  Pure integer code
+    (tableau.py:103-123 order), no device needed."""
+    return [lam for lam in _generate_partitions(n) if lam[0] >= n - k]
+
+
+_SMALL_PARTITIONS = {
+    1: [(1,)], 2: [(2,), (1, 1)], 3: [(3,), (2, 1), (1, 1, 1)], 4: [(4,), (3, 1), (2, 2), (2, 1, 1), (1, 1, 1, 1)],
+    5: [(5,), (4, 1), (3, 2), (3, 1, 1), (2, 2, 1), (2, 1, 1, 1), (1, 1, 1, 1, 1)],
+}
+
+
+def _generate_partitions(n: int):
+    """generate_partitions(n) of the reference (tableau.py:103-123): hard-coded lists for n <= 5, else (n,) followed by
+    sorted((k, *p)) for k = 1..n-1 and p a partition of n-k, first occurrence kept."""
+    if n in _SMALL_PARTITIONS:
+        return list(_SMALL_PARTITIONS[n])
+    out = [(n,)]
+    seen = {(n,)}
+    for k in range(1, n):
+        for p in _generate_partitions(n - k):
+            q = tuple(sorted((k, *p), reverse=True))
+            if q not in seen:
+                seen.add(q)
+                out.append(q)
+    return out
+
+
+def sn_fft_bandlimited(fn_vals: torch.Tensor, n: int, k: int = None, partitions=None) -> dict:
+    """Forward transform restricted to a subset of the partitions: the partitions with
+    lambda_1 >= n - k, or an explicit list `partitions`.  Returns {partition: F(partition)} for those partitions
+    only, equal to the same entries of sn_fft(fn_vals, n), in generate_partitions order.  The level steps k >= 8
+    compute only the shapes contained in a selected partition, so a small band costs a fraction of the full
+    transform (about 40 % at n = 10, k <= 3)."""
+    _check_input(fn_vals, n)
+    if (k is None) == (partitions is None):
+        raise ValueError("give either k or partitions")
+    x, home = _to_device(fn_vals)
+    lead = tuple(x.shape[:-1])
+    f2d = x.reshape(-1, x.shape[-1]).contiguous()
+    batch = f2d.shape[0]
+    plan = get_plan(n, f2d.dtype, f2d.device)
+    if partitions is None:
+        if not isinstance(k, int) or k < 0:
+            raise ValueError("k must be a non-negative integer")
+        wanted = [lam for lam in plan.partitions if lam[0] >= n - k]
+    else:
+        wanted = [tuple(int(v) for v in lam) for lam in partitions]
+        bad = [lam for lam in wanted if lam not in plan.index]
+        if bad:
+            raise ValueError(f"{bad[0]} is not a partition of {n}")
+    idx = sorted({plan.index[lam] for lam in wanted})
+    sub = plan.subplan(idx)
+    if plan.subplan_info(sub)[1] > _SUBSET_MAX_FRACTION:
+        _, packed = _forward_packed(f2d, n)            # a wide band: the full pipeline is faster, select afterwards
+    else:
+        packed = torch.empty(batch * plan.nfact, dtype=f2d.dtype, device=f2d.device)
+    if batch and plan.subplan_info(sub)[1] <= _SUBSET_MAX_FRACTION:
+        with _device_ctx(f2d.device):
+            ws = plan.workspace(batch)
+            _lib.check(_lib.load().snfft_forward_subset(plan.handle, sub, f2d.data_ptr(), batch, packed.data_ptr(),
+                                                        ws.data_ptr(), ws.numel(), _stream_ptr(f2d.device)),
+                       "snfft_forward_subset")
+    result = {}
+    for p in idx:
+        lam, d, off = plan.partitions[p], plan.dims[p], plan.offsets[p]
+        blk = packed[off * batch:(off + d * d) * batch]
+        if d == 1:
+            val = blk.view(lead)
+        else:
+            val = blk.view(lead + (d, d))
+            if n <= BASE_CASE:
+                val = val.squeeze()
+        # a small band is cloned out of the n!-sized packed buffer so that the buffer can be freed
+        val = val.clone() if plan.offsets[-1] > 8 * sum(plan.dims[q] ** 2 for q in idx) else val
+        result[lam] = val if home == x.device else val.to(home)
+    return result
+
+
+def sn_ifft_bandlimited(ft: dict, n: int) -> torch.Tensor:
+    """Inverse transform of a band-limited coefficient dict: the partitions missing from `ft` count as zero,
+        f(sigma) = 1/n! sum_{lambda in ft} d_lambda <F(lambda), rho_lambda(sigma)>
+    -- the projection of a function onto the isotypic components present in `ft`, e.g.
+    sn_ifft_bandlimited(sn_fft_bandlimited(f, n, k=1), n) is the first-order (one-point marginal) approximation of f."""
+    if not ft:
+        raise ValueError("ft is empty")
+    some = next(iter(ft.values()))
+    if not isinstance(some, torch.Tensor):
+        raise TypeError("ft must map partitions to tensors")
+    x, home = _to_device(some)
+    if x.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"only float32 and float64 are supported, got {x.dtype}")
+    plan = get_plan(n, x.dtype, x.device)
+    keys = [tuple(int(v) for v in lam) for lam in ft]
+    bad = [lam for lam in keys if lam not in plan.index]
+    if bad:
+        raise ValueError(f"{bad[0]} is not a partition of {n}")
+    first = plan.index[keys[0]]
+    d0 = plan.dims[first]
+    t0 = ft[list(ft)[0]]
+    batch = t0.numel() // (d0 * d0)
+    lead = tuple(t0.shape) if d0 == 1 else tuple(t0.shape[:-2])
+    if n <= BASE_CASE and math.prod(lead or (1,)) != batch:
+        lead = (batch,) if batch != 1 else ()
+    packed = torch.zeros(batch * plan.nfact, dtype=x.dtype, device=x.device)
+    for lam, v in zip(keys, ft.values()):
+        p = plan.index[lam]
+        d, off = plan.dims[p], plan.offsets[p]
+        if v.numel() != batch * d * d:
+            raise ValueError(f"ft[{lam}] has {v.numel()} elements, expected {batch * d * d}")
+        packed[off * batch:(off + d * d) * batch].copy_(v.to(device=x.device, dtype=x.dtype).reshape(-1))
+    out = _inverse_subset_packed(plan, plan.subplan([plan.index[lam] for lam in keys]), packed, batch).view(lead + (plan.nfact,))
+    if n <= BASE_CASE:
+        out = out.squeeze()
+    return out if home == out.device else out.to(home)
 
 
 def calc_power(ft: dict, n: int) -> dict:

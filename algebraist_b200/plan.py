@@ -39,6 +39,28 @@ class Plan:
         self.index = {p: i for i, p in enumerate(self.partitions)}
         self.nfact = math.factorial(n)
         assert self.offsets[-1] == self.nfact
+        self._subplans = {}
+        self._sub_lock = threading.Lock()
+
+    def subplan(self, keep_indices):
+        """Handle of the subset plan (snfft_subplan_create) for the partitions with these indices, cached per plan."""
+        key = tuple(sorted(set(int(i) for i in keep_indices)))
+        if not key or key[0] < 0 or key[-1] >= len(self.partitions):
+            raise ValueError("bad partition subset")
+        with self._sub_lock:
+            h = self._subplans.get(key)
+            if h is None:
+                mask = (ctypes.c_int32 * len(self.partitions))(*[1 if i in set(key) else 0 for i in range(len(self.partitions))])
+                h = ctypes.c_void_p()
+                _lib.check(_lib.load().snfft_subplan_create(self.handle, mask, ctypes.byref(h)), "snfft_subplan_create")
+                self._subplans[key] = h
+            return h
+
+    def subplan_info(self, handle):
+        k = ctypes.c_int()
+        frac = ctypes.c_double()
+        _lib.check(_lib.load().snfft_subplan_info(handle, ctypes.byref(k), ctypes.byref(frac)), "snfft_subplan_info")
+        return k.value, frac.value
 
     def workspace(self, batch: int) -> torch.Tensor:
         nbytes = _lib.load().snfft_workspace_bytes(self.handle, batch)
@@ -46,10 +68,19 @@ class Plan:
 
     def __del__(self):
         try:
+            for h in getattr(self, "_subplans", {}).values():
+                _lib.load().snfft_subplan_destroy(h)
             if self.handle:
                 _lib.load().snfft_plan_destroy(self.handle)
         except Exception:
             pass
+
+
+def clear_plan_cache():
+    """Drop every cached plan (and its device tables).  The kernel-family choices of a plan are fixed when it is
+    created (debug hooks, SNFFT_* environment switches), so call this after changing one of them."""
+    with _cache_lock:
+        _cache.clear()
 
 
 def get_plan(n: int, dtype: torch.dtype, device: torch.device) -> Plan:

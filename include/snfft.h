@@ -165,6 +165,27 @@ int snfft_forward_cosets2(const snfft_plan_t* plan_n, const snfft_plan_t* plan_n
                           size_t workspace_bytes, void* stream);
 
 /*
+ * Transforms restricted to a subset of the partitions of n (band-limited transforms, e.g. the
+ * partitions with lambda_1 >= n - k of ranking / grokking analyses, README.md:11,32).  `keep[q] != 0` selects
+ * partition q of the plan (snfft_plan_info order).  The forward transform computes F(lambda) for the kept
+ * partitions only (the other blocks of the packed output are zero); the inverse returns
+ *   f(sigma) = 1/n! sum_{lambda kept} d_lambda <F(lambda), rho_lambda(sigma)>
+ * and ignores the blocks of the other partitions -- with one kept partition that is a component of
+ * sn_fourier_decomposition (fourier.py:291-295).  Level steps k >= 8 only touch the shapes contained in a kept
+ * partition (Young's lattice down-closure); the levels below run the plan's ordinary kernels.  Same buffers
+ * and workspace as snfft_forward / snfft_inverse.  A subset plan belongs to the plan it was created from and
+ * must be destroyed before it.
+ */
+typedef struct snfft_subplan snfft_subplan_t;
+int snfft_subplan_create(const snfft_plan_t* plan, const int32_t* keep, snfft_subplan_t** out);
+void snfft_subplan_destroy(snfft_subplan_t* sub);
+int snfft_subplan_info(const snfft_subplan_t* sub, int* first_pruned_level, double* kept_fraction);
+int snfft_forward_subset(const snfft_plan_t* plan, const snfft_subplan_t* sub, const void* f, int64_t B, void* F,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int snfft_inverse_subset(const snfft_plan_t* plan, const snfft_subplan_t* sub, const void* F, int64_t B, void* f,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Group-action utilities on the device.
  *   rho       : out[d][d] (row major, device) = rho_lambda(sigma) in Young's orthogonal form for the partition
  *               with index `part` of the plan's level n, sigma a one-line permutation of range(n) (host array)
@@ -217,12 +238,14 @@ int snfft_dense_rep(snfft_plan_t* plan, int part, void* out, void* stream);
  * launches is bracketed by an event pair; _end synchronises on them and returns
  * one aggregated record per (kind, level, kernel class).
  *   kind: 0 forward level, 1 inverse level, 2 input gather, 3 output scatter,
- *         4 forward base kernels (level = 5: levels 2..5 in registers; level = 6: level 6),
- *         5 inverse base kernels (same levels), 6 pack (top level -> [lambda][B][d][d]), 7 unpack
- *   kernel_class: 0..5 sweep-per-pass classes, >= 10 the fused-top / register-bottom (TB) kernels, -1 generated base kernels, -2 data
- *         movement, -3 the register column kernels (levels 6..8, forward level 9: col_kernels.cuh)
+ *         4 forward base kernel (level = 5: levels 2..5 in registers), 5 inverse base kernel,
+ *         6 pack (top level -> [lambda][B][d][d]), 7 unpack
+ *   kernel_class: 0..5 table-driven sweep-kernel classes, -1 generated base kernel / scalar data movement,
+ *         -2 vectorised data movement, -3 register column kernels (levels 6..8: col_kernels.cuh),
+ *         -4 / -5 the Z / T kernel of a top / bottom level step (levels 9..11: tz_kernels.cuh),
+ *         -6 small-batch gather / scatter and the B = 1 pack copy
  *   elems_per_instance: coefficients the launch produces per function
- *     (its share of k!; the launch reads as many), so its algorithmic traffic
+ *     (its share of k!; the launch reads as many; the Z kernel: MB/k of k!), so its algorithmic traffic
  *     is 2 * elems_per_instance * NINST_level * sizeof(dtype) bytes.
  */
 typedef struct snfft_profile_record {
@@ -241,17 +264,14 @@ int64_t snfft_launch_count(void);
  * Affects plans created afterwards.  Lets small n exercise every kernel class. */
 void snfft_debug_force_class(int cls);
 
-/* Test hook: how levels 2..6 run for n > 5.  0 = generated register kernels
- * (default), 1 = per-level table-driven kernels, 2 = table-driven shared-memory
- * base kernel; all three must agree, so every path stays covered. */
+/* Test hook: how levels 2..5 run for n > 5.  0 = generated register kernel (default), != 0 = the per-level
+ * table-driven sweep kernels at EVERY level; both must agree, so the second implementation stays covered.
+ * Read at every call. */
 void snfft_debug_disable_base(int mode);
 
-/* Test hook: which kernels run the level steps k >= 7 (and every level when the
- * base kernels are disabled).  -1 = automatic (fused-top / register-bottom "TB"
- * kernels with s = 1, 1, 2, 3 fused sweeps at k = 7, 8, 9, 10, sweep-per-pass
- * kernels elsewhere), 0 = sweep-per-pass kernels only, 1..3 = TB kernels with
- * that many fused top sweeps wherever such a kernel is compiled.  Affects plans
- * created afterwards; both families must agree with the oracle. */
+/* Test hook: which kernels run the level steps k >= 6.  -1 = automatic (generated column kernels at k = 6..8,
+ * top / bottom kernels at k = 9..11, table-driven sweep kernels above), >= 0 = sweep kernels only.  Affects plans
+ * created afterwards (the Python plan cache: algebraist_b200.plan.clear_plan_cache); both must agree with the oracle. */
 void snfft_debug_tb_mode(int mode);
 
 /* Test hook: 1 = the input gather / output scatter always run the scalar tile kernel (the one used for

@@ -46,14 +46,14 @@ def _worker(rank, world, port, n, batch, emu_path, out_dir):
         local = sn_fft_batch_sharded(f, n)
         lo, hi = shard_bounds(batch, world, rank)
         back = sn_ifft_batch_sharded(local, n)
-        assert torch.allclose(back.reshape(hi - lo, -1), f[lo:hi], atol=1e-12)
+        assert torch.allclose(back.reshape(hi - lo, f.shape[1]), f[lo:hi], atol=1e-12)
         full = sn_fft_batch_sharded(f, n, gather=True)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{"_".join(map(str, k)): v.numpy() for k, v in full.items()})
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,batch", [(6, 5), (4, 4)])
+@pytest.mark.parametrize("n,batch", [(6, 5), (4, 4), (6, 1)])
 def test_batch_sharding_world2_gloo(tmp_path, n, batch):
     from oracle import sn_oracle as O
     emu_path = build_emu()

@@ -60,8 +60,9 @@ def test_every_kernel_class(emu, cls, dt):
 
 @pytest.mark.parametrize("dt", ["f64", "f32"])
 @pytest.mark.parametrize("B", [1, 5, 37])
-def test_fused_base_kernel_equals_level_kernels(emu, dt, B):
-    """n = 7: levels 2..6 run in the fused shared-memory base kernel; the per-level path must agree."""
+def test_generated_kernels_equal_sweep_kernels(emu, dt, B):
+    """n = 7: levels 2..5 in the generated register kernel and 6, 7 in the column kernels; the table-driven
+    per-level sweep kernels (debug hook 1) must agree."""
     n = 7
     rng = np.random.default_rng(B)
     f = rng.standard_normal((B, math.factorial(n))).astype(DT[dt])
@@ -162,19 +163,15 @@ def test_launch_counter(emu):
     assert emu.snfft_launch_count() - before >= 4      # gather + levels 2..4
 
 
-# (n, tb mode, base mode): which fused-top / register-bottom ("TB") kernel the level steps run.
-# mode -1 is the product's automatic choice, 0 the sweep-per-pass kernels, 1..3 force s fused top sweeps;
-# base 1 sends the levels <= 6 through the level kernels too, so small n reaches every (MB, s) combination.
-# Since the column kernels (col_kernels.cuh) own levels 7 and 8 in automatic mode, mode -1 at n = 7, 8 checks THEM
-# against the oracle and mode 1 keeps the TB kernels with one fused sweep covered.
-TB_CASES = [(7, -1, 0), (7, 1, 0), (7, 2, 0), (7, 3, 0), (6, 1, 1), (6, 2, 1), (6, 3, 1), (5, 1, 1), (8, -1, 0), (8, 1, 0),
-            (8, 2, 0), (8, 3, 0)]
+# (n, kernel mode, base mode): mode -1 is the product's automatic choice (column kernels at levels 6..8), mode 0 the
+# table-driven sweep kernels; base 1 sends the levels <= 5 through the sweep kernels too.
+FAMILY_CASES = [(7, -1, 0), (7, 0, 0), (6, 0, 1), (5, 0, 1), (8, -1, 0), (8, 0, 0), (8, 0, 1)]
 
 
-@pytest.mark.parametrize("n,mode,base", TB_CASES)
+@pytest.mark.parametrize("n,mode,base", FAMILY_CASES)
 @pytest.mark.parametrize("dt", ["f64", "f32"])
-def test_tb_kernels_vs_oracle(emu, n, mode, base, dt):
-    """Fused-top / register-bottom level kernels (level_tb.cuh) against the oracle, forward and inverse."""
+def test_kernel_families_vs_oracle(emu, n, mode, base, dt):
+    """Both implementations of the level steps against the oracle, forward, inverse of arbitrary coefficients, round trip."""
     B = 1 if n == 8 else 3
     rng = np.random.default_rng(10 * n + mode)
     f = rng.standard_normal((B, math.factorial(n))).astype(DT[dt])
@@ -198,9 +195,9 @@ def test_tb_kernels_vs_oracle(emu, n, mode, base, dt):
         emu.snfft_plan_destroy(plan)
 
 
-def test_level9_forward_column_kernels_vs_oracle(emu):
-    """n = 9 in automatic mode: the forward step k = 9 runs the four-part column kernels (col_gen_9p*.cuh), the
-    inverse step the sweep kernels; both against the oracle on one function."""
+def test_level9_top_bottom_kernels_vs_oracle(emu):
+    """n = 9 in automatic mode: the level step k = 9 runs the top / bottom kernels (tz_kernels.cuh: level-7 column
+    operators on pieces of the inputs, then the two top sweeps) in both directions; against the oracle on one function."""
     n, B = 9, 1
     rng = np.random.default_rng(9)
     f = rng.standard_normal((B, math.factorial(n)))
@@ -217,13 +214,13 @@ def test_level9_forward_column_kernels_vs_oracle(emu):
         emu.snfft_plan_destroy(plan)
 
 
-def test_tb_and_sweep_kernels_agree_ragged_batch(emu):
+def test_column_and_sweep_kernels_agree_ragged_batch(emu):
     """Odd batch (scalar transfer path, ragged last tile): both kernel families give the same coefficients."""
     n, B = 7, 5
     rng = np.random.default_rng(7)
     f = rng.standard_normal((B, math.factorial(n)))
     outs = []
-    for mode in (0, 1, 3):
+    for mode in (0, -1):
         emu.snfft_debug_tb_mode(mode)
         abi = CAbi(emu)
         plan = abi.plan(n, np.float64)
@@ -234,7 +231,7 @@ def test_tb_and_sweep_kernels_agree_ragged_batch(emu):
             assert rel_err(abi.inverse(plan, packed, B), f) < 1e-12
         finally:
             emu.snfft_plan_destroy(plan)
-    assert rel_err(outs[1], outs[0]) < 1e-13 and rel_err(outs[2], outs[0]) < 1e-13
+    assert rel_err(outs[1], outs[0]) < 1e-13
 
 
 @pytest.mark.parametrize("n,B,dt", [(4, 4, "f32"), (6, 8, "f32"), (7, 36, "f32"), (5, 2, "f64"), (6, 18, "f64")])
@@ -259,28 +256,4 @@ def test_vector_gather_scatter(emu, n, B, dt):
         assert rel_err(back, f) < TOL[dt]
     finally:
         emu.snfft_debug_scalar_gather(0)
-        emu.snfft_plan_destroy(plan)
-
-
-def test_tb_forward_persistent_tiles(emu, monkeypatch):
-    """The forward TB kernel walks over several tiles per CTA (tables staged once, the next tile's inputs
-    prefetched behind the last B phase): with the grid capped at one CTA per task every tile goes through
-    the loop, and the result must not change."""
-    n, B = 7, 44
-    rng = np.random.default_rng(44)
-    f = rng.standard_normal((B, math.factorial(n)))
-    abi = CAbi(emu)
-    plan = abi.plan(n, np.float64)
-    try:
-        ref = abi.forward(plan, f)
-        monkeypatch.setenv("SNFFT_TB_GX", "1")
-        one = abi.forward(plan, f)
-        monkeypatch.setenv("SNFFT_TB_GX", "2")
-        two = abi.forward(plan, f)
-        assert np.array_equal(ref, one) and np.array_equal(ref, two)
-        want = O.sn_fft_packed(f[:2], n)
-        got = unpack(ref, n, B)
-        for lam in want:
-            assert rel_err(got[lam][:2], want[lam]) < 1e-12, lam
-    finally:
         emu.snfft_plan_destroy(plan)
