@@ -31,6 +31,7 @@ from gen_base import Emitter, ScaledEmitter, boffs, children, coef_off, dim, par
 
 LEVELS = (6, 7, 8)
 CHILD_MAJOR_MAX = 6       # levels whose tasks keep a whole child column in registers
+INV_COSETS_PER_TASK = int(os.environ.get("SNFFT_GEN_INV_COSETS", "2"))   # adjacent cosets per inverse task at levels 7, 8
 SPLIT_FWD = {9: 4}        # forward-only levels, generated as several headers / translation units / launches
 
 
@@ -144,6 +145,70 @@ def inverse_task(em, k, mu, i, rows, load, store, unit_scale=False):
             em.lines.append("    SNFFT_CODE_FENCE();")     # one block's loads at a time
     for r in rows:
         store(r, acc[r])
+
+
+def inverse_task_multi(em, k, mu, cosets, rows, load, store, unit_scale=False):
+    """inverse_task for several cosets at once: rows `rows` of G^(i)_mu[:, c] for every i in `cosets`.  The chains of
+    the cosets share nothing but their INPUTS -- and those are what the inverse kernels are short of: one task per
+    coset re-reads every parent column k times (58-65 % L2 hit rate, profiles r02h).  A block of a parent column is
+    loaded once (the union of the rows the cosets need), then every coset runs its own bottom sweeps on it and adds
+    its term of the top sweep to its own running sums.  store(i, r, value)."""
+    dm = dim(mu)
+    acc = {(i, r): None for i in cosets for r in rows}
+    for lam in partitions(k):
+        ch = children(lam)
+        if mu not in ch:
+            continue
+        b = ch.index(mu)
+        bo, dl = boffs(lam)[b], dim(lam)
+        scale = 1.0 if unit_scale else dl / (k * dm)
+        want = [bo + r for r in rows]
+        top = {}
+        for t in want:
+            q, dist = partner_checked(lam, k - 2, t)
+            if q == t:
+                top[t] = [(float(dist), t)]
+            else:
+                top[t] = [(1.0 / dist, t), (math.sqrt(1.0 - 1.0 / (dist * dist)), q)]
+        by_block = {}
+        for t in want:
+            for coef, src in top[t]:
+                by_block.setdefault(block_of(lam, src), []).append((t, coef, src))
+        for blk in sorted(by_block, key=lambda x: (x != b, x)):       # the block of mu first
+            terms = by_block[blk]
+            plans = []                      # per coset: (i, bottom sweeps, need chain) for this block
+            for i in cosets:
+                if i > k - 2:               # coset k-1: identity, only the rows of the block of mu itself
+                    if blk == b:
+                        plans.append((i, None, None))
+                    continue
+                seq = list(range(i, k - 2))
+                plans.append((i, seq, need_chain(lam, seq, sorted({src for _, _, src in terms}))))
+            rows_needed = set()
+            for i, seq, need in plans:
+                rows_needed |= set(want) if seq is None else need[0]
+            loaded = {t: (1.0, load(lam, t, bo)) for t in sorted(rows_needed)}
+            for i, seq, need in plans:
+                if seq is None:
+                    for r in rows:
+                        acc[(i, r)] = em.lin([(1.0, acc[(i, r)]), (scale, loaded[bo + r])])
+                    continue
+                x = {t: loaded[t] for t in need[0]}
+                for m, j in enumerate(seq):
+                    x = sweep_need(em, lam, j, x, need[m + 1])
+                for t, coef, src in terms:
+                    if x.get(src) is not None:
+                        acc[(i, t - bo)] = em.lin([(1.0, acc[(i, t - bo)]), (scale * coef, x[src])])
+            em.lines.append("    SNFFT_CODE_FENCE();")     # one block's loads at a time
+    for i in cosets:
+        for r in rows:
+            store(i, r, acc[(i, r)])
+
+
+def coset_groups(k, size):
+    """Cosets 0..k-1 in runs of `size` adjacent ones: adjacent cosets need nearly the same rows (the rows coset i + 1
+    needs are a subset of those coset i needs), so a run loads little more than its first member."""
+    return [list(range(a, min(a + size, k))) for a in range(0, k, size)]
 
 
 def value_expr(v):
@@ -267,21 +332,21 @@ def gen_level(k, inverse, only=None):
             # one task per (row set, coset i): a function that ran all k chains would keep the addresses of the rows of
             # F_lambda (the same in every chain) live throughout and spill
             for rows in row_sets(7, mu):                 # all rows of mu: the block of mu in F_lambda is then read once
-                for i in range(k):
+                for grp in coset_groups(k, INV_COSETS_PER_TASK):
                     em = ScaledEmitter()
 
                     def load(lam, t, bo, em=em):
                         return em.tmp(f"in[(size_t){coef_off(lam) + t * dim(lam) + bo} * s]")
 
-                    def store(r, v, em=em, i=i, dm=dm):
+                    def store(i, r, v, em=em, dm=dm):
                         em.lines.append(f"    out[(size_t){r * dm * k + i} * s] = {value_expr(v)};")
 
-                    inverse_task(em, k, mu, i, rows, load, store)
+                    inverse_task_multi(em, k, mu, grp, rows, load, store)
                     total += em.n
                     funcs.append("\n".join([
                         "template <typename T>",
                         f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned s) {{"
-                        f"   // {mu}, rows {rows[0]}..{rows[-1]}, coset {i}"] + em.lines + ["}"]) + "\n")
+                        f"   // {mu}, rows {rows[0]}..{rows[-1]}, cosets {grp[0]}..{grp[-1]}"] + em.lines + ["}"]) + "\n")
                     cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)c * s, out + (size_t)({coef_off(mu)} + c) * {k} * s, s); break;")
                     task += 1
         groups.append((dm, task0, task - task0))

@@ -36,7 +36,8 @@ import math
 import os
 
 from gen_base import ScaledEmitter, boffs, children, coef_off, dim, partitions
-from gen_col import forward_task, inverse_task, need_chain, row_sets, sweep_need, value_expr, write_if_changed
+from gen_col import (INV_COSETS_PER_TASK, coset_groups, forward_task, inverse_task_multi, need_chain, row_sets, sweep_need,
+                     value_expr, write_if_changed)
 
 LEVEL_MB = {9: 7, 10: 7, 11: 8}        # level k -> bottom level MB (the Z kernel runs level-MB column operators)
 LEVELS = tuple(LEVEL_MB)
@@ -77,7 +78,7 @@ def _aoff(zeta, alpha):
 # ----------------------------------------------------------------------------
 def gen_z(MB, inverse):
     """Level-MB column operators.  Forward: one task per (zeta, parent alpha, row set of alpha): all rows for
-    MB = 7, one child block of alpha for MB = 8 (as in gen_col.py).  Inverse: one task per (zeta, coset i)."""
+    MB = 7, one child block of alpha for MB = 8 (as in gen_col.py).  Inverse: one task per (zeta, run of adjacent cosets)."""
     tag = f"zb{MB}{'i' if inverse else 'f'}"
     funcs, cases, groups = [], [], []
     task = 0
@@ -108,21 +109,21 @@ def gen_z(MB, inverse):
                 cases.append(f"        case {task}: {tag}_{task}<T>(in, out, rs, s, zs); break;")
                 task += 1
         else:
-            for i in range(MB):
+            for grp in coset_groups(MB, INV_COSETS_PER_TASK):
                 em = ScaledEmitter()
 
                 def load(alpha, t, bo, em=em, zeta=zeta):
                     return em.tmp(f"in[(size_t){aoff(zeta, alpha) + t} * zs]")
 
-                def store(r, v, em=em, i=i):
+                def store(i, r, v, em=em):
                     em.lines.append(f"    out[(size_t){r} * rs + (size_t){i} * s] = {value_expr(v)};")
 
-                inverse_task(em, MB, zeta, i, list(range(dz)), load, store, unit_scale=True)
+                inverse_task_multi(em, MB, zeta, grp, list(range(dz)), load, store, unit_scale=True)
                 total += em.n
                 funcs.append("\n".join([
                     "template <typename T>",
                     f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned rs, unsigned s, unsigned zs) {{"
-                    f"   // {zeta}, coset {i}"] + em.lines + ["}"]) + "\n")
+                    f"   // {zeta}, cosets {grp[0]}..{grp[-1]}"] + em.lines + ["}"]) + "\n")
                 cases.append(f"        case {task}: {tag}_{task}<T>(in, out, rs, s, zs); break;")
                 task += 1
         groups.append((dz, task0, task - task0))
