@@ -33,11 +33,10 @@ def tz_deps(kind):
 # top / bottom kernels (csrc/tz_tu.cu): kind 7 / 8 = Z kernel with that bottom level, 9 / 10 / 11 = T kernel of that level
 TZ_COMBOS = [(kind, f64, inv) for kind in (8, 7, 11, 10, 9) for f64 in (0, 1) for inv in (0, 1)]
 COL_COMBOS = [(k, f64, inv) for k in (6, 7, 8) for f64 in (0, 1) for inv in (0, 1)]
-COL9_PARTS = 4        # level 9, forward only: gen_col.SPLIT_FWD
 # threads per CTA of the column kernels by (level, fp64); default 128.  One large CTA per SM keeps all its warps on
 # the code of ONE task (instruction fetch was the top stall at levels 8 and 9 with five 128-thread CTAs of
 # different tasks per SM): forward k = 9 3.36 -> 2.30 ms, fp64 5.6 -> 3.7 ms; level 7 is faster with 128.
-COL_THREADS = {(9, 0): 640, (8, 0): 640, (9, 1): 384, (8, 1): 384}
+COL_THREADS = {(8, 0): 640, (8, 1): 384}
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
@@ -48,11 +47,6 @@ def units():
           [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}",
            f"-DSNFFT_COL_THREADS={COL_THREADS.get((k, f64), 128)}"], col_deps(k))
          for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
-    u = [(os.path.join(OBJ, f"col_9p{p}_{'f64' if f64 else 'f32'}_fwd_t{COL_THREADS.get((9, f64), 128)}.o"), os.path.join(CSRC, "col_tu.cu"),
-          ["-DSNFFT_COL_K=9", f"-DSNFFT_COL_PART={p}", f"-DSNFFT_COL_F64={f64}", "-DSNFFT_COL_INV=0",
-           f"-DSNFFT_COL_THREADS={COL_THREADS.get((9, f64), 128)}"],
-          [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", f"col_gen_9p{p}.cuh")])
-         for f64 in (0, 1) for p in range(COL9_PARTS)] + u
     u += [(os.path.join(OBJ, f"tz_{kind}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "tz_tu.cu"),
            [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"], tz_deps(kind))
           for kind, f64, inv in TZ_COMBOS]
@@ -65,7 +59,7 @@ def generate_col_headers(force: bool = False):
     """col_gen_<k>.cuh (20 MB of straight-line code) are not kept in git: csrc/gen_col.py writes them (2 s)."""
     for script, gen_names, head_names in (
             ("gen_col.py", ("gen_col.py", "gen_base.py"),
-             [f"col_gen_{k}.cuh" for k in (6, 7, 8)] + [f"col_gen_9p{p}.cuh" for p in range(COL9_PARTS)]),
+             [f"col_gen_{k}.cuh" for k in (6, 7, 8)]),
             ("gen_tz.py", ("gen_tz.py", "gen_col.py", "gen_base.py"),
              ["tz_gen_z7.cuh", "tz_gen_z8.cuh", "tz_gen_tab.cuh", "tz_gen_t9.cuh", "tz_gen_t10.cuh", "tz_gen_t11.cuh"])):
         gens = [os.path.join(CSRC, f) for f in gen_names]

@@ -1,5 +1,4 @@
-// Column kernels for the level steps k = 6, 7, 8 and the forward step k = 9 (generated code col_gen_<k>.cuh,
-// gen_col.py; level 9 is generated in parts = separate translation units and launches over disjoint child shapes).
+// Column kernels for the level steps k = 6, 7, 8 (generated code col_gen_<k>.cuh, gen_col.py).
 // A thread is (task, column c, instance): it owns the rows of one output column that the bottom sweeps keep
 // together (<= 35 values) in registers, reads its inputs straight from the level array below (lanes over
 // consecutive instances: every global access is a contiguous run) and writes its rows once.  Forward task:
@@ -15,7 +14,7 @@
 #include <stdint.h>
 
 #ifndef SNFFT_COL_K
-#error "col_kernels.cuh: define SNFFT_COL_K (6..9) -- one translation unit per level (level 9: per part)"
+#error "col_kernels.cuh: define SNFFT_COL_K (6..8) -- one translation unit per level"
 #endif
 #if SNFFT_COL_K == 6
 #include "col_gen_6.cuh"
@@ -23,14 +22,6 @@
 #include "col_gen_7.cuh"
 #elif SNFFT_COL_K == 8
 #include "col_gen_8.cuh"
-#elif SNFFT_COL_K == 9 && SNFFT_COL_PART == 0
-#include "col_gen_9p0.cuh"
-#elif SNFFT_COL_K == 9 && SNFFT_COL_PART == 1
-#include "col_gen_9p1.cuh"
-#elif SNFFT_COL_K == 9 && SNFFT_COL_PART == 2
-#include "col_gen_9p2.cuh"
-#elif SNFFT_COL_K == 9 && SNFFT_COL_PART == 3
-#include "col_gen_9p3.cuh"
 #endif
 
 namespace snfft {

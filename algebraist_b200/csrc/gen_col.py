@@ -31,8 +31,16 @@ from gen_base import Emitter, ScaledEmitter, boffs, children, coef_off, dim, par
 
 LEVELS = (6, 7, 8)
 CHILD_MAJOR_MAX = 6       # levels whose tasks keep a whole child column in registers
-INV_COSETS_PER_TASK = int(os.environ.get("SNFFT_GEN_INV_COSETS", "2"))   # adjacent cosets per inverse task at levels 7, 8
-SPLIT_FWD = {9: 4}        # forward-only levels, generated as several headers / translation units / launches
+# adjacent cosets per inverse task by level (the Z kernels of gen_tz.py use the entry of their bottom level MB):
+# measured on a B200 (profiles r02l/r02m), bounded by the registers the running sums need (no spills at level 7 up
+# to 4 cosets = 64 sums; level 8 spills beyond 2)
+PREFETCH = os.environ.get("SNFFT_GEN_PREFETCH", "1") != "0"      # issue a chain's / block's loads one step ahead of the arithmetic
+INV_COSETS_PER_TASK = {7: int(os.environ.get("SNFFT_GEN_INV_COSETS_7", "4")), 8: int(os.environ.get("SNFFT_GEN_INV_COSETS_8", "2"))}
+SPLIT_FWD = {}            # forward-only levels generated in parts (level 9, until the top / bottom kernels of gen_tz.py took it over)
+# forward tasks: rows of output a task owns at most (level 8: adjacent child blocks are merged up to this many rows,
+# so that small blocks share their loads; level 7: several parents of one child shape per task, as many as fit this
+# many running sums)
+FWD_ROWS_CAP = {7: int(os.environ.get("SNFFT_GEN_FWD_ROWS_7", "70")), 8: int(os.environ.get("SNFFT_GEN_FWD_ROWS_8", "35"))}
 
 
 def partner_checked(part, j, t):
@@ -76,21 +84,76 @@ def forward_task(em, k, lam, b, rows, load, store):
     mu = children(lam)[b]
     bo, dm = boffs(lam)[b], dim(mu)
     acc = {t: None for t in rows}
+    needs = [need_chain(lam, list(range(k - 2, i - 1, -1)), rows) for i in range(k)]
+
+    def fetch(i):                       # the loads of coset i, issued one chain ahead (PREFETCH): with ~20 warps per SM the
+        return {bo + r: (1.0, load(r, i)) for r in range(dm) if bo + r in needs[i][0]}     # latency of a chain's loads is not hidden otherwise
+
+    nxt = fetch(0)
     for i in range(k):
         seq = list(range(k - 2, i - 1, -1))
-        need = need_chain(lam, seq, rows)
-        x = {}
-        for r in range(dm):
-            if bo + r in need[0]:
-                x[bo + r] = (1.0, load(r, i))
+        need = needs[i]
+        x = nxt
+        nxt = fetch(i + 1) if PREFETCH and i + 1 < k else None
         for m, j in enumerate(seq):
             x = sweep_need(em, lam, j, x, need[m + 1])
         for t in rows:
             if x.get(t) is not None:
                 acc[t] = em.lin([(1.0, acc[t]), (1.0, x[t])])
-        em.lines.append("    SNFFT_CODE_FENCE();")     # keeps the loads of the next chain below this one (register pressure)
+        em.lines.append("    SNFFT_CODE_FENCE();")     # keeps the loads of the chains after the next one below this one (register pressure)
+        if nxt is None and i + 1 < k:
+            nxt = fetch(i + 1)
     for t in rows:
         store(t, acc[t])
+
+
+def forward_task_multi(em, k, targets, load, store):
+    """forward_task for several parents of ONE child shape at once.  targets = [(lam, b, rows)], all with the same
+    children(lam)[b]; store(ti, t, value).  The chains of the parents share nothing but their inputs: a coset's piece
+    of the child column is loaded once and every parent runs its own sweeps on it (the sibling tasks of forward_task
+    re-read it from L2, one load per parent)."""
+    mu = children(targets[0][0])[targets[0][1]]
+    dm = dim(mu)
+    acc = [{t: None for t in rows} for _, _, rows in targets]
+    needs = [[need_chain(lam, list(range(k - 2, i - 1, -1)), rows) for lam, b, rows in targets] for i in range(k)]
+
+    def fetch(i):                       # rows of the child column any parent needs from coset i, loaded once
+        rows_in = sorted({r for ti, (lam, b, rows) in enumerate(targets) for r in range(dm) if boffs(lam)[b] + r in needs[i][ti][0]})
+        return {r: load(r, i) for r in rows_in}
+
+    nxt = fetch(0)
+    for i in range(k):
+        seq = list(range(k - 2, i - 1, -1))
+        cache = nxt
+        nxt = fetch(i + 1) if PREFETCH and i + 1 < k else None     # one coset ahead of the arithmetic
+        for ti, (lam, b, rows) in enumerate(targets):
+            assert children(lam)[b] == mu
+            bo = boffs(lam)[b]
+            need = needs[i][ti]
+            x = {bo + r: (1.0, cache[r]) for r in range(dm) if bo + r in need[0]}
+            for m, j in enumerate(seq):
+                x = sweep_need(em, lam, j, x, need[m + 1])
+            for t in rows:
+                if x.get(t) is not None:
+                    acc[ti][t] = em.lin([(1.0, acc[ti][t]), (1.0, x[t])])
+        em.lines.append("    SNFFT_CODE_FENCE();")     # keeps the loads of later chains below this one (register pressure)
+        if nxt is None and i + 1 < k:
+            nxt = fetch(i + 1)
+    for ti, (lam, b, rows) in enumerate(targets):
+        for t in rows:
+            store(ti, t, acc[ti][t])
+
+
+def parent_groups(mu, cap):
+    """The parents of `mu` in groups whose dimensions add up to at most `cap` running sums (largest with smallest)."""
+    ps = sorted([lam for lam in partitions(sum(mu) + 1) if mu in children(lam)], key=dim, reverse=True)
+    groups = []
+    while ps:
+        g = [ps.pop(0)]
+        while ps and sum(dim(x) for x in g) + dim(ps[-1]) <= cap:
+            g.append(ps.pop())
+        groups.append(sorted(g, key=lambda lam: partitions(sum(lam)).index(lam)))
+    return groups
 
 
 def block_of(lam, t):
@@ -152,9 +215,11 @@ def inverse_task_multi(em, k, mu, cosets, rows, load, store, unit_scale=False):
     the cosets share nothing but their INPUTS -- and those are what the inverse kernels are short of: one task per
     coset re-reads every parent column k times (58-65 % L2 hit rate, profiles r02h).  A block of a parent column is
     loaded once (the union of the rows the cosets need), then every coset runs its own bottom sweeps on it and adds
-    its term of the top sweep to its own running sums.  store(i, r, value)."""
+    its term of the top sweep to its own running sums.  The loads of the next block are issued before the arithmetic
+    of the current one (PREFETCH).  store(i, r, value)."""
     dm = dim(mu)
     acc = {(i, r): None for i in cosets for r in rows}
+    work = []                               # (lam, bo, scale, terms, plans, rows to load) per block of a parent column
     for lam in partitions(k):
         ch = children(lam)
         if mu not in ch:
@@ -187,19 +252,31 @@ def inverse_task_multi(em, k, mu, cosets, rows, load, store, unit_scale=False):
             rows_needed = set()
             for i, seq, need in plans:
                 rows_needed |= set(want) if seq is None else need[0]
-            loaded = {t: (1.0, load(lam, t, bo)) for t in sorted(rows_needed)}
-            for i, seq, need in plans:
-                if seq is None:
-                    for r in rows:
-                        acc[(i, r)] = em.lin([(1.0, acc[(i, r)]), (scale, loaded[bo + r])])
-                    continue
-                x = {t: loaded[t] for t in need[0]}
-                for m, j in enumerate(seq):
-                    x = sweep_need(em, lam, j, x, need[m + 1])
-                for t, coef, src in terms:
-                    if x.get(src) is not None:
-                        acc[(i, t - bo)] = em.lin([(1.0, acc[(i, t - bo)]), (scale * coef, x[src])])
-            em.lines.append("    SNFFT_CODE_FENCE();")     # one block's loads at a time
+            if plans:
+                work.append((lam, bo, scale, terms, plans, sorted(rows_needed)))
+
+    def fetch(w):
+        lam, bo, _, _, _, rows_needed = work[w]
+        return {t: (1.0, load(lam, t, bo)) for t in rows_needed}
+
+    nxt = fetch(0) if work else None
+    for w, (lam, bo, scale, terms, plans, _) in enumerate(work):
+        loaded = nxt
+        nxt = fetch(w + 1) if PREFETCH and w + 1 < len(work) else None
+        for i, seq, need in plans:
+            if seq is None:
+                for r in rows:
+                    acc[(i, r)] = em.lin([(1.0, acc[(i, r)]), (scale, loaded[bo + r])])
+                continue
+            x = {t: loaded[t] for t in need[0]}
+            for m, j in enumerate(seq):
+                x = sweep_need(em, lam, j, x, need[m + 1])
+            for t, coef, src in terms:
+                if x.get(src) is not None:
+                    acc[(i, t - bo)] = em.lin([(1.0, acc[(i, t - bo)]), (scale * coef, x[src])])
+        em.lines.append("    SNFFT_CODE_FENCE();")     # at most two blocks' loads live at a time
+        if nxt is None and w + 1 < len(work):
+            nxt = fetch(w + 1)
     for i in cosets:
         for r in rows:
             store(i, r, acc[(i, r)])
@@ -225,7 +302,14 @@ def row_sets(k, part):
     if k <= 7:
         return [list(range(d))]
     if k == 8:
-        return [list(range(o, o + dim(c))) for c, o in zip(children(part), boffs(part))]
+        out, cap = [], FWD_ROWS_CAP[8]
+        for c, o in zip(children(part), boffs(part)):       # adjacent child blocks, merged while they fit the cap
+            blk = list(range(o, o + dim(c)))
+            if out and len(out[-1]) + len(blk) <= cap:
+                out[-1] += blk
+            else:
+                out.append(blk)
+        return out
     out = []                    # k = 9: the blocks two levels down (partitions of 7, <= 35 rows)
     for c, o in zip(children(part), boffs(part)):
         out += [list(range(o + o2, o + o2 + dim(c2))) for c2, o2 in zip(children(c), boffs(c))]
@@ -302,6 +386,27 @@ def gen_level(k, inverse, only=None):
                 f"   // {mu}, every coset"] + em.lines + ["}"]) + "\n")
             cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)c * s, out + (size_t)({coef_off(mu)} + c) * {k} * s, s); break;")
             task += 1
+        elif not inverse and k == 7:
+            # one task per group of parents: every coset's piece of the child column is loaded once per group
+            for grp in parent_groups(mu, FWD_ROWS_CAP[7]):
+                em = ScaledEmitter()
+                targets = [(lam, children(lam).index(mu), list(range(dim(lam)))) for lam in grp]
+
+                def load(r, i, em=em, dm=dm):
+                    return em.tmp(f"in[(size_t){r * dm * k + i} * s]")
+
+                def store(ti, t, v, em=em, targets=targets):
+                    lam, b, _ = targets[ti]
+                    em.lines.append(f"    out[(size_t){coef_off(lam) + t * dim(lam) + boffs(lam)[b]} * s] = {value_expr(v)};")
+
+                forward_task_multi(em, k, targets, load, store)
+                total += em.n
+                funcs.append("\n".join([
+                    "template <typename T>",
+                    f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned s) {{"
+                    f"   // {', '.join(str(l) for l in grp)} <- {mu}"] + em.lines + ["}"]) + "\n")
+                cases.append(f"        case {task}: {tag}_{task}<T>(in + (size_t)({coef_off(mu)} + c) * {k} * s, out + (size_t)c * s, s); break;")
+                task += 1
         elif not inverse:
             for lam in partitions(k):
                 if mu not in children(lam):
@@ -332,7 +437,7 @@ def gen_level(k, inverse, only=None):
             # one task per (row set, coset i): a function that ran all k chains would keep the addresses of the rows of
             # F_lambda (the same in every chain) live throughout and spill
             for rows in row_sets(7, mu):                 # all rows of mu: the block of mu in F_lambda is then read once
-                for grp in coset_groups(k, INV_COSETS_PER_TASK):
+                for grp in coset_groups(k, INV_COSETS_PER_TASK[k]):
                     em = ScaledEmitter()
 
                     def load(lam, t, bo, em=em):

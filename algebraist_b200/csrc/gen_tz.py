@@ -36,8 +36,8 @@ import math
 import os
 
 from gen_base import ScaledEmitter, boffs, children, coef_off, dim, partitions
-from gen_col import (INV_COSETS_PER_TASK, coset_groups, forward_task, inverse_task_multi, need_chain, row_sets, sweep_need,
-                     value_expr, write_if_changed)
+from gen_col import (FWD_ROWS_CAP, INV_COSETS_PER_TASK, coset_groups, forward_task, forward_task_multi, inverse_task_multi,
+                     need_chain, parent_groups, row_sets, sweep_need, value_expr, write_if_changed)
 
 LEVEL_MB = {9: 7, 10: 7, 11: 8}        # level k -> bottom level MB (the Z kernel runs level-MB column operators)
 LEVELS = tuple(LEVEL_MB)
@@ -86,7 +86,26 @@ def gen_z(MB, inverse):
     for zeta in partitions(MB - 1):
         dz = dim(zeta)
         task0 = task
-        if not inverse:
+        if not inverse and MB == 7:
+            for grp in parent_groups(zeta, FWD_ROWS_CAP[7]):       # several parents per task: inputs loaded once per group
+                em = ScaledEmitter()
+                targets = [(alpha, children(alpha).index(zeta), list(range(dim(alpha)))) for alpha in grp]
+
+                def load(r, i, em=em):
+                    return em.tmp(f"in[(size_t){r} * rs + (size_t){i} * s]")
+
+                def store(ti, t, v, em=em, targets=targets, zeta=zeta):
+                    em.lines.append(f"    out[(size_t){aoff(zeta, targets[ti][0]) + t} * zs] = {value_expr(v)};")
+
+                forward_task_multi(em, MB, targets, load, store)
+                total += em.n
+                funcs.append("\n".join([
+                    "template <typename T>",
+                    f"__device__ __noinline__ void {tag}_{task}(const T* __restrict__ in, T* __restrict__ out, unsigned rs, unsigned s, unsigned zs) {{"
+                    f"   // {', '.join(str(a) for a in grp)} <- {zeta}"] + em.lines + ["}"]) + "\n")
+                cases.append(f"        case {task}: {tag}_{task}<T>(in, out, rs, s, zs); break;")
+                task += 1
+        elif not inverse:
             for alpha in parents(zeta):
               for rows in row_sets(MB, alpha):
                 em = ScaledEmitter()
@@ -109,7 +128,7 @@ def gen_z(MB, inverse):
                 cases.append(f"        case {task}: {tag}_{task}<T>(in, out, rs, s, zs); break;")
                 task += 1
         else:
-            for grp in coset_groups(MB, INV_COSETS_PER_TASK):
+            for grp in coset_groups(MB, INV_COSETS_PER_TASK[MB]):
                 em = ScaledEmitter()
 
                 def load(alpha, t, bo, em=em, zeta=zeta):

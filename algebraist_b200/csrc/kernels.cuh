@@ -1160,19 +1160,35 @@ __global__ void __launch_bounds__(256) translate_kernel(const T* __restrict__ f,
 // ---------------------------------------------------------------------------
 // Per-partition products of two packed coefficient arrays: C_lambda[b] = A_lambda[b] . B_lambda[b]
 // (d x d, row major), the Fourier side of the convolution theorem (reference tests/test_fourier.py:87-109).
-// One launch per partition; a CTA owns a 64 x 64 tile of one batch row, 256 threads x (4 x 4) outputs,
+// One launch for all partitions; a CTA owns a 64 x 64 tile of one batch row of one partition, 256 threads x (4 x 4) outputs,
 // K in steps of 16 through shared memory (A stored transposed so both operand reads are conflict free).
 // Plain FFMA / DFMA: the parity contract is fp32 1e-5 / fp64 1e-12, which rules out the TF32 tensor path.
 // ---------------------------------------------------------------------------
 constexpr int MM_TILE = 64, MM_K = 16, MM_THREADS = 256;
 
+// ONE launch for every partition: the partitions are listed largest first (the long CTAs start early), blk0 = first
+// CTA of each, off = its offset in the packed arrays (B * coef_off)
+constexpr int MM_MAXPARTS = 80;          // 77 partitions at n = 12
+struct MMParts {
+    int nparts;
+    int d[MM_MAXPARTS];
+    long long blk0[MM_MAXPARTS + 1];
+    long long off[MM_MAXPARTS];
+};
+
 template <typename T>
 __global__ void __launch_bounds__(MM_THREADS) block_matmul_kernel(const T* __restrict__ A, const T* __restrict__ B,
-                                                                  T* __restrict__ C, int d, int tiles) {
+                                                                  T* __restrict__ C, const MMParts mp) {
     __shared__ T As[MM_K][MM_TILE + 4];
     __shared__ T Bs[MM_K][MM_TILE + 4];
     const int tid = threadIdx.x;
-    const long long blk = blockIdx.x;
+    int part = 0;
+    while (part + 1 < mp.nparts && (long long)blockIdx.x >= mp.blk0[part + 1]) ++part;
+    const int d = mp.d[part], tiles = (d + MM_TILE - 1) / MM_TILE;
+    A += mp.off[part];
+    B += mp.off[part];
+    C += mp.off[part];
+    const long long blk = (long long)blockIdx.x - mp.blk0[part];
     const long long b = blk / ((long long)tiles * tiles);
     const int rem = (int)(blk - b * (long long)tiles * tiles);
     const int m0 = (rem / tiles) * MM_TILE, n0 = (rem % tiles) * MM_TILE;

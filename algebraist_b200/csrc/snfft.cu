@@ -637,13 +637,8 @@ extern "C" {
 SNFFT_COL_DECL(6, f32) SNFFT_COL_DECL(6, f64) SNFFT_COL_DECL(7, f32) SNFFT_COL_DECL(7, f64) SNFFT_COL_DECL(8, f32)
 SNFFT_COL_DECL(8, f64)
 #undef SNFFT_COL_DECL
-#define SNFFT_COL9_DECL(p) \
-    int snfft_col_launch_9p##p##_f32_fwd(const void*, void*, long long, cudaStream_t); \
-    int snfft_col_launch_9p##p##_f64_fwd(const void*, void*, long long, cudaStream_t);
-SNFFT_COL9_DECL(0) SNFFT_COL9_DECL(1) SNFFT_COL9_DECL(2) SNFFT_COL9_DECL(3)
-#undef SNFFT_COL9_DECL
 }
-constexpr int kColFirst = 6, kColLast = 9, kColLastInv = 8;      // level 9: forward only, four launches
+constexpr int kColFirst = 6, kColLast = 8, kColLastInv = 8;
 
 // Levels that use the column kernels: automatic kernel choice only (the forced TB / sweep modes of
 // snfft_debug_tb_mode keep testing the sweep kernels), SNFFT_COL_FWD / SNFFT_COL_INV (lists of levels) override.
@@ -659,20 +654,6 @@ static int run_col_level(const snfft_plan* p, int k, const void* in, void* out, 
     const long long ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
     ProfScope prof(p, st, INVERSE ? 1 : 0, k, -3, p->host.factorial[k]);
     int rc;
-    if (k == 9) {                       // forward only: one launch per set of child shapes
-        if (INVERSE) return set_error(SNFFT_ENOTSUP, "no inverse column kernel at level 9");
-        typedef int (*fn_t)(const void*, void*, long long, cudaStream_t);
-        static const fn_t f32[4] = {snfft_col_launch_9p0_f32_fwd, snfft_col_launch_9p1_f32_fwd, snfft_col_launch_9p2_f32_fwd,
-                                    snfft_col_launch_9p3_f32_fwd};
-        static const fn_t f64[4] = {snfft_col_launch_9p0_f64_fwd, snfft_col_launch_9p1_f64_fwd, snfft_col_launch_9p2_f64_fwd,
-                                    snfft_col_launch_9p3_f64_fwd};
-        for (int part = 0; part < 4; ++part) {
-            rc = (sizeof(T) == 4 ? f32 : f64)[part](in, out, ninst, st);
-            g_launches.fetch_add(1);
-            if (rc) return set_error(SNFFT_ECUDA, std::string("column kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
-        }
-        return SNFFT_OK;
-    }
 #define SNFFT_COL_CALL(kk, dt) (INVERSE ? snfft_col_launch_##kk##_##dt##_inv(in, out, ninst, st) : snfft_col_launch_##kk##_##dt##_fwd(in, out, ninst, st))
     if (sizeof(T) == 4) rc = k == 6 ? SNFFT_COL_CALL(6, f32) : (k == 7 ? SNFFT_COL_CALL(7, f32) : SNFFT_COL_CALL(8, f32));
     else rc = k == 6 ? SNFFT_COL_CALL(6, f64) : (k == 7 ? SNFFT_COL_CALL(7, f64) : SNFFT_COL_CALL(8, f64));
@@ -1486,22 +1467,32 @@ int snfft_block_matmul(const snfft_plan_t* p, const void* A, const void* Bm, voi
     if (!A || !Bm || !C) return set_error(SNFFT_EINVAL, "NULL data pointer");
     const HostLevel& L = p->host.levels[p->n];
     cudaStream_t st = (cudaStream_t)stream;
-    for (size_t q = 0; q < L.shapes.size(); ++q) {
-        const int d = L.shapes[q].dim;
-        const int tiles = (d + MM_TILE - 1) / MM_TILE;
-        const long long nblk = (long long)B * tiles * tiles;
-        if (nblk > 0x7fffffffll) return set_error(SNFFT_ENOTSUP, "snfft_block_matmul: batch too large");
-        const size_t off = (size_t)L.coef_offsets[q] * (size_t)B;
-        dim3 grid((unsigned)nblk, 1, 1), block(MM_THREADS, 1, 1);
-        if (p->dtype == SNFFT_F32) {
-            auto kfn = block_matmul_kernel<float>;
-            SNFFT_LAUNCH(kfn, grid, block, 0, st, (const float*)A + off, (const float*)Bm + off, (float*)C + off, d, tiles);
-        } else {
-            auto kfn = block_matmul_kernel<double>;
-            SNFFT_LAUNCH(kfn, grid, block, 0, st, (const double*)A + off, (const double*)Bm + off, (double*)C + off, d, tiles);
-        }
-        g_launches.fetch_add(1);
+    if (L.shapes.size() > (size_t)MM_MAXPARTS) return set_error(SNFFT_ENOTSUP, "snfft_block_matmul: too many partitions");
+    std::vector<int> order(L.shapes.size());
+    for (size_t q = 0; q < order.size(); ++q) order[q] = (int)q;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return L.shapes[x].dim > L.shapes[y].dim; });
+    MMParts mp;
+    mp.nparts = (int)order.size();
+    long long nblk = 0;
+    for (size_t i = 0; i < order.size(); ++i) {
+        const int d = L.shapes[order[i]].dim;
+        const long long tiles = (d + MM_TILE - 1) / MM_TILE;
+        mp.d[i] = d;
+        mp.blk0[i] = nblk;
+        mp.off[i] = (long long)L.coef_offsets[order[i]] * (long long)B;
+        nblk += (long long)B * tiles * tiles;
     }
+    mp.blk0[order.size()] = nblk;
+    if (nblk > 0x7fffffffll) return set_error(SNFFT_ENOTSUP, "snfft_block_matmul: batch too large");
+    dim3 grid((unsigned)nblk, 1, 1), block(MM_THREADS, 1, 1);
+    if (p->dtype == SNFFT_F32) {
+        auto kfn = block_matmul_kernel<float>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const float*)A, (const float*)Bm, (float*)C, mp);
+    } else {
+        auto kfn = block_matmul_kernel<double>;
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const double*)A, (const double*)Bm, (double*)C, mp);
+    }
+    g_launches.fetch_add(1);
     SNFFT_CUDA(cudaGetLastError());
     return SNFFT_OK;
 }
