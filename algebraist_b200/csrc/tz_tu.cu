@@ -199,18 +199,22 @@ extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_
     }
     for (int t = L::ntasks; t <= T_MAXTASKS; ++t) g.blk0[t] = (unsigned)blk;
     if (blk > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    int s_shift = -1;
+    if ((ninst & (ninst - 1)) == 0)
+        for (s_shift = 0; (1ll << s_shift) < ninst; ++s_shift) {
+        }
     dim3 grid((unsigned)blk, 1, 1), block(T_THREADS, 1, 1);
 #if SNFFT_TZ_INV
 #define TZ_T_LAUNCH(VT)                                                                                   \
     {                                                                                                     \
         auto kfn = t_kernel<VT, SNFFT_TZ_KIND, true>;                                                     \
-        SNFFT_LAUNCH(kfn, grid, block, 0, st, (VT*)z, (VT*)x, (const VT*)xk, (unsigned)ninst, g);         \
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (VT*)z, (VT*)x, (const VT*)xk, (unsigned)ninst, s_shift, g);         \
     }
 #else
 #define TZ_T_LAUNCH(VT)                                                                                   \
     {                                                                                                     \
         auto kfn = t_kernel<VT, SNFFT_TZ_KIND, false>;                                                    \
-        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const VT*)z, (const VT*)x, (VT*)xk, (unsigned)ninst, g);   \
+        SNFFT_LAUNCH(kfn, grid, block, 0, st, (const VT*)z, (const VT*)x, (VT*)xk, (unsigned)ninst, s_shift, g);   \
     }
 #endif
     if (nv == 4) {

@@ -33,15 +33,17 @@ def main():
             fam[f"col_kernel<{t}, {k}, 1>"] = f"inv_level_k{k}_c-3"
     # top / bottom kernels: the T kernel names its level and direction; the Z kernel (level-7 operators) runs for
     # k = 9 and 10 in a fixed order inside one forward + inverse: forward 9, forward 10, inverse 10, inverse 9
-    for t in ("float", "double"):
-        for k in (9, 10, 11):
-            for pat_t in (t, f"TzVec<{t}, 4>", f"TzVec<{t}, 2>"):
-                fam[f"t_kernel<{pat_t}, {k}, 0>"] = f"fwd_level_k{k}_c-5"
-                fam[f"t_kernel<{pat_t}, {k}, 1>"] = f"inv_level_k{k}_c-5"
+    import re
+    tpat = re.compile(r"t_kernel<.*?(float|double)(?:, \d)?>?, (\d+), ([01])>")
     zorder = {"0": ["fwd_level_k9_c-4", "fwd_level_k10_c-4"], "1": ["inv_level_k10_c-4", "inv_level_k9_c-4"]}
     zseen = {"0": 0, "1": 0}
     best = {}
     for r in rows[1:]:
+        m = tpat.search(r[ki])
+        if m:
+            name = f"{'inv' if m.group(3) == '1' else 'fwd'}_level_k{m.group(2)}_c-5"
+            best[name] = (float(r[ti].split()[0]), to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
+            continue
         if "z_kernel<" in r[ki]:
             inv = "1" if (", 1>" in r[ki] or "true>" in r[ki]) else "0"
             if zseen[inv] < len(zorder[inv]):
