@@ -63,8 +63,8 @@ struct ZGroups {
 #if SNFFT_TZ_KIND == 7 || SNFFT_TZ_KIND == 8
 template <typename T, bool INV>
 __global__ void __launch_bounds__(Z_THREADS, (sizeof(T) == 4 ? 640 : 384) / Z_THREADS)
-z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, const ZGroups g, const ZSeg* __restrict__ segs,
-         const unsigned* __restrict__ unit2seg) {
+z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, int s_shift, const ZGroups g,
+         const ZSeg* __restrict__ segs, const unsigned* __restrict__ unit2seg) {
     const unsigned b = blockIdx.x;
     int gi = 0;
     while (gi + 1 < g.ngroups && b >= g.blk0[gi + 1]) ++gi;
@@ -82,7 +82,10 @@ z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, const ZGrou
     const unsigned long long q = (unsigned long long)tile * Z_THREADS + threadIdx.x;
     if (q >= qn) return;
     unsigned u, inst;
-    if ((q >> 32) == 0) {
+    if (s_shift >= 0) {                 // NINST_k a power of two
+        u = (unsigned)(q >> s_shift);
+        inst = (unsigned)q & (s - 1u);
+    } else if ((q >> 32) == 0) {
         u = (unsigned)q / s;
         inst = (unsigned)q - u * s;
     } else {
@@ -146,9 +149,11 @@ __host__ __device__ __forceinline__ TzVec<S, NV> operator-(const TzVec<S, NV>& a
     for (int i = 0; i < NV; ++i) r.v[i] = -a.v[i];
     return r;
 }
+constexpr int T_HINTS = 512;
 struct TTasks {
-    int ntasks;
+    int ntasks, hint_shift;
     unsigned blk0[T_MAXTASKS + 1];       // first block of every task (d_alpha, d_mu per task: TzDev<K>, generated)
+    unsigned short hint[T_HINTS + 1];    // hint[j] = the task that owns block j << hint_shift: the search starts there
 };
 
 #if SNFFT_TZ_KIND >= 9
@@ -160,7 +165,9 @@ __global__ void __launch_bounds__(T_THREADS, 2)
 t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::conditional<INV, T*, const T*>::type xb,
          typename std::conditional<INV, const T*, T*>::type lb, unsigned s, int s_shift, const TTasks g) {
     const unsigned b = blockIdx.x;
-    int lo = 0, hi = g.ntasks - 1;               // last task with blk0 <= b
+    // last task with blk0 <= b, searched between the hints of this block's bucket (usually zero or one step:
+    // a full binary search over the tasks was a third of this kernel's instructions)
+    int lo = g.hint[b >> g.hint_shift], hi = g.hint[(b >> g.hint_shift) + 1];
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (g.blk0[mid] <= b) lo = mid;

@@ -164,7 +164,11 @@ extern "C" int TZ_ZNAME(int k, const void* src, void* dst, long long ninst, cuda
     if (blk == 0) return 0;
     dim3 grid((unsigned)blk, 1, 1), block(Z_THREADS, 1, 1);
     auto kfn = z_kernel<tz_t, SNFFT_TZ_INV != 0>;
-    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const tz_t*)src, (tz_t*)dst, (unsigned)ninst, g, (const ZSeg*)d->segs,
+    int s_shift = -1;
+    if ((ninst & (ninst - 1)) == 0)
+        for (s_shift = 0; (1ll << s_shift) < ninst; ++s_shift) {
+        }
+    SNFFT_LAUNCH(kfn, grid, block, 0, st, (const tz_t*)src, (tz_t*)dst, (unsigned)ninst, s_shift, g, (const ZSeg*)d->segs,
                  (const unsigned*)d->unit2seg);
     return (int)cudaGetLastError();
 }
@@ -199,6 +203,13 @@ extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_
     }
     for (int t = L::ntasks; t <= T_MAXTASKS; ++t) g.blk0[t] = (unsigned)blk;
     if (blk > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    g.hint_shift = 0;
+    while ((blk >> g.hint_shift) >= (unsigned long long)T_HINTS) ++g.hint_shift;
+    for (int j = 0, t = 0; j <= T_HINTS; ++j) {          // owner of block j << hint_shift (clamped to the last task)
+        const unsigned long long b0 = (unsigned long long)j << g.hint_shift;
+        while (t + 1 < L::ntasks && g.blk0[t + 1] <= b0) ++t;
+        g.hint[j] = (unsigned short)t;
+    }
     int s_shift = -1;
     if ((ninst & (ninst - 1)) == 0)
         for (s_shift = 0; (1ll << s_shift) < ninst; ++s_shift) {
