@@ -40,7 +40,10 @@ struct ColGroups {
     int task0[COL_MAXGROUPS], ntask[COL_MAXGROUPS], dmu[COL_MAXGROUPS];
 };
 
-template <int K, bool INV>
+// threads per CTA of the F2 instantiation (two instances per thread, the register footprint of the fp64 one)
+constexpr int COL_THREADS_V2 = COL_THREADS > 384 ? 384 : COL_THREADS;
+
+template <int K, bool INV, int NT = COL_THREADS>
 inline ColGroups col_groups(long long ninst, int chunk) {
     using I = ColInfo<K, INV>;
     static_assert(I::ngroups <= COL_MAXGROUPS, "too many groups");
@@ -53,7 +56,7 @@ inline ColGroups col_groups(long long ninst, int chunk) {
         g.task0[i] = I::task0()[i];
         g.ntask[i] = I::ntask()[i];
         g.dmu[i] = I::dmu()[i];
-        const long long tiles = ((long long)g.dmu[i] * ninst + COL_THREADS - 1) / COL_THREADS;
+        const long long tiles = ((long long)g.dmu[i] * ninst + NT - 1) / NT;
         blk += (unsigned long long)tiles * g.ntask[i];
     }
     for (int i = I::ngroups; i <= COL_MAXGROUPS; ++i) g.blk0[i] = (unsigned)blk;
@@ -63,8 +66,8 @@ inline ColGroups col_groups(long long ninst, int chunk) {
 
 // Register cap: ptxas hoists the (read-only) loads of a whole task as far as the register file allows, which without
 // a cap means 255 registers and spills; MINB CTAs per SM bound it (fp32: 102 registers, fp64: 170).
-template <typename T, int K, bool INV>
-__global__ void __launch_bounds__(COL_THREADS, (sizeof(T) == 4 ? 640 : 384) / COL_THREADS) col_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst,
+template <typename T, int K, bool INV, int NT = COL_THREADS>
+__global__ void __launch_bounds__(NT, (sizeof(T) == 4 ? 640 : 384) / NT) col_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst,
                                                           const ColGroups g) {
     const unsigned b = blockIdx.x;
     int gi = 0;
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(COL_THREADS, (sizeof(T) == 4 ? 640 : 384) / CO
     const unsigned local = b - g.blk0[gi];
     const unsigned nt = (unsigned)g.ntask[gi];
     const long long qn = (long long)g.dmu[gi] * ninst;
-    const unsigned ntiles = (unsigned)((qn + COL_THREADS - 1) / COL_THREADS);
+    const unsigned ntiles = (unsigned)((qn + NT - 1) / NT);
     const unsigned per = (unsigned)g.chunk * nt;              // blocks of a full chunk
     const unsigned ch = local / per, r = local - ch * per;
     const unsigned left = ntiles - ch * (unsigned)g.chunk;    // tiles of this chunk (the last one may be short)
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(COL_THREADS, (sizeof(T) == 4 ? 640 : 384) / CO
     const unsigned tk = r / cht;
     const unsigned tile = ch * (unsigned)g.chunk + (r - tk * cht);
     const int task = g.task0[gi] + (int)tk;
-    const long long q = (long long)tile * COL_THREADS + threadIdx.x;
+    const long long q = (long long)tile * NT + threadIdx.x;
     if (q >= qn) return;
     const int c = (int)(q / ninst);
     const long long inst = q - (long long)c * ninst;

@@ -9,6 +9,7 @@
 #define SNFFT_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 
@@ -50,6 +51,31 @@ extern "C" int COL_NAME(const void* in, void* out, long long ninst, cudaStream_t
         // level 9 forward 4 tiles, level 8 16 (fp64: 8), level 7 inverse 74, otherwise one wave of 148
         return SNFFT_COL_K == 9 ? 4 : (SNFFT_COL_K == 8 ? (SNFFT_COL_F64 ? 8 : 16) : (SNFFT_COL_K == 7 && SNFFT_COL_INV ? 74 : 148));
     }();
+#if !SNFFT_COL_F64
+    // fp32: two adjacent instances per thread as one F2 (vec2.cuh: 8-byte transfers, FFMA2) when the instance count and
+    // the buffers allow it; SNFFT_COL_V2=0 keeps the scalar threads (bit-identical results)
+    static const bool v2_on = [] {
+        const char* e = std::getenv("SNFFT_COL_V2");
+        return !e || std::atoi(e) != 0;
+    }();
+    if (v2_on && ninst % 2 == 0 && ((uintptr_t)in | (uintptr_t)out) % sizeof(F2) == 0) {
+        static const int chunk2 = [] {
+            char name[32];
+            std::snprintf(name, sizeof name, "SNFFT_COL_CHUNK2_%d", SNFFT_COL_K);
+            const char* e = std::getenv(name);
+            if (e) return std::atoi(e);
+            return SNFFT_COL_K == 8 ? 8 : (SNFFT_COL_K == 7 && SNFFT_COL_INV ? 37 : 74);
+        }();
+        const long long n2 = ninst / 2;
+        const ColGroups g2 = col_groups<SNFFT_COL_K, SNFFT_COL_INV != 0, COL_THREADS_V2>(n2, chunk2);
+        if (n2 >= (1ll << 32) || g2.total > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+        if (g2.total == 0) return 0;
+        dim3 grid2((unsigned)g2.total, 1, 1), block2(COL_THREADS_V2, 1, 1);
+        auto kfn2 = col_kernel<F2, SNFFT_COL_K, SNFFT_COL_INV != 0, COL_THREADS_V2>;
+        SNFFT_LAUNCH(kfn2, grid2, block2, 0, st, (const F2*)in, (F2*)out, n2, g2);
+        return (int)cudaGetLastError();
+    }
+#endif
     const ColGroups g = col_groups<SNFFT_COL_K, SNFFT_COL_INV != 0>(ninst, chunk);
     // the kernels use a 32-bit row stride and a one-dimensional grid
     if (ninst >= (1ll << 32) || g.total > 0x7fffffffull) return (int)cudaErrorInvalidValue;

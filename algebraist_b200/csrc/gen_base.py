@@ -203,7 +203,7 @@ class ScaledEmitter(Emitter):
             elif r == -1.0:
                 expr = f"{expr} - {name}"
             else:
-                expr = f"{self.lit(r)} * {name} + {expr}"
+                expr = f"sn_fma({self.lit(r)}, {name}, {expr})"     # vec2.cuh: FFMA / DFMA, FFMA2 for pairs of instances
         return (s0, self.tmp(expr))
 
 
@@ -338,7 +338,7 @@ def main():
     here = os.path.dirname(os.path.abspath(__file__))
     parts = ["// GENERATED by gen_base.py -- do not edit.  Straight-line Young's-orthogonal-form code for the",
              "// lowest levels of the S_n FFT (see gen_base.py for the derivation and reference citations).",
-             "#pragma once", "#include <stddef.h>", "",
+             "#pragma once", "#include <stddef.h>", "#include \"vec2.cuh\"", "",
              "// keeps the loads of one column from being hoisted above the stores of the previous one",
              "// (otherwise the register allocator sees every column of the level at once and spills)",
              "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")", "", "namespace snfft {", ""]

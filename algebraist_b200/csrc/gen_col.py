@@ -475,7 +475,7 @@ def gen_level(k, inverse, only=None):
 def header(k, codes, run_lines):
     parts = [f"// GENERATED by gen_col.py -- do not edit.  Register column code of the level step k = {k}",
              "// (see gen_col.py for the derivation and the reference citations).",
-             "#pragma once", "#include <stddef.h>", "",
+             "#pragma once", "#include <stddef.h>", "#include \"vec2.cuh\"", "",
              "#ifndef SNFFT_CODE_FENCE",
              "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")",
              "#endif", "",

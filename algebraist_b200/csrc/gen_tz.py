@@ -235,9 +235,9 @@ def t_forward(em, k, mu, alpha):
             for offp in outs:
                 acc[offp] = em.lin([(1.0, acc[offp]), (1.0, x.get(offp))])
         for offp in outs:
-            stores.append(f"    ob{li}[(size_t){coef_off(lam) + offp * dl + bo} * s] = {value_expr(acc[offp])};")
+            stores.append(f"    ob{li}.st({offp * dl + bo}u, {value_expr(acc[offp])});")
     em.lines += stores
-    return [(li, dim(lam)) for li, lam in enumerate(parents(mu))
+    return [(li, dim(lam), coef_off(lam)) for li, lam in enumerate(parents(mu))
             if any(Pp[-1] == alpha for Pp, _ in subblocks(lam, s))]
 
 
@@ -256,10 +256,10 @@ def t_inverse(em, k, mu, alpha):
         outs = [offp for Pp, offp in subblocks(lam, s) if Pp[-1] == alpha]
         if not outs:
             continue
-        used.append((li, dim(lam)))
+        used.append((li, dim(lam), coef_off(lam)))
         bo, dl = boffs(lam)[children(lam).index(mu)], dim(lam)
         for offp in outs:
-            loads[(li, offp)] = em.tmp(f"ib{li}[(size_t){coef_off(lam) + offp * dl + bo} * s]")
+            loads[(li, offp)] = em.tmp(f"ib{li}.ld({offp * dl + bo}u)")
     for li, lam in enumerate(parents(mu)):
         outs = [offp for Pp, offp in subblocks(lam, s) if Pp[-1] == alpha]
         if not outs:
@@ -309,21 +309,23 @@ def gen_t(k, inverse):
         dmu = dim(mu)
         cq = "" if inverse else "const "
         cl = "const " if inverse else ""
+        # the level-k side goes through TzAcc (tz_kernels.cuh): PK = false the level array X_k, PK = true the public
+        # packed layout [lambda][B][d][d] (top level only: the pack / unpack pass is fused into this kernel)
         head = [
-            "template <typename T>",
-            f"__device__ __noinline__ void {tag}_{task}({cq}T* __restrict__ zb, {cq}T* __restrict__ xb, {cl}T* __restrict__ lb, unsigned r, unsigned c, unsigned s) {{"
+            "template <typename T, bool PK>",
+            f"__device__ __noinline__ void {tag}_{task}({cq}T* __restrict__ zb, {cq}T* __restrict__ xb, {cl}T* __restrict__ lb, unsigned r, unsigned c, unsigned s, unsigned inst) {{"
             f"   // mu = {mu}, alpha = {alpha}",
             f"    zb += (size_t)(r * {dmu}u + c) * s;",
             f"    xb += (size_t)(r * {dmu}u + c) * {k}u * s;"]
-        for li, dl in used:
-            head.append(f"    {cl}T* __restrict__ {'ib' if inverse else 'ob'}{li} = lb + (size_t)(r * {dl}u + c) * s;")
+        for li, dl, co in used:
+            head.append(f"    const TzAcc<T, PK, {'true' if inverse else 'false'}> {'ib' if inverse else 'ob'}{li}(lb, {co}u, {dl}u, r, c, s, inst);")
         funcs.append("\n".join(head + em.lines + ["}"]) + "\n")
-        cases.append(f"        case {task}: {tag}_{task}<T>(zb, xb, lb, r, c, s); break;")
+        cases.append(f"        case {task}: {tag}_{task}<T, PK>(zb, xb, lb, r, c, s, inst); break;")
     code = funcs
     code.append("\n".join([
-        "template <typename T>",
+        "template <typename T, bool PK>",
         f"__device__ __forceinline__ void {tag}_run(int task, {'' if inverse else 'const '}T* __restrict__ zb, {'' if inverse else 'const '}T* __restrict__ xb, "
-        f"{'const ' if inverse else ''}T* __restrict__ lb, unsigned r, unsigned c, unsigned s) {{",
+        f"{'const ' if inverse else ''}T* __restrict__ lb, unsigned r, unsigned c, unsigned s, unsigned inst) {{",
         "    switch (task) {"] + cases + ["        default: break;", "    }", "}"]) + "\n")
     return "\n".join(code), total
 
@@ -356,7 +358,7 @@ def level_tables(k):
     return "\n".join(lines) + "\n"
 
 
-HEAD = ["#pragma once", "#include <stddef.h>", "",
+HEAD = ["#pragma once", "#include <stddef.h>", "#include \"vec2.cuh\"", "",
         "#ifndef SNFFT_CODE_FENCE",
         "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")",
         "#endif", "",
@@ -392,10 +394,10 @@ def main():
             f"template <> struct TzDev<{k}> {{",
             f"    static __device__ __forceinline__ unsigned dal(int t) {{ return tz{k}_dal[t]; }}",
             f"    static __device__ __forceinline__ unsigned dmu(int t) {{ return tz{k}_dmu[t]; }}",
-            "    template <typename T, bool INV, typename PZ, typename PL>",
-            "    static __device__ __forceinline__ void run(int task, PZ zb, PZ xb, PL lb, unsigned r, unsigned c, unsigned s) {",
-            f"        if constexpr (!INV) tz{k}f_run<T>(task, zb, xb, lb, r, c, s);",
-            f"        else tz{k}i_run<T>(task, zb, xb, lb, r, c, s);",
+            "    template <typename T, bool INV, bool PK, typename PZ, typename PL>",
+            "    static __device__ __forceinline__ void run(int task, PZ zb, PZ xb, PL lb, unsigned r, unsigned c, unsigned s, unsigned inst) {",
+            f"        if constexpr (!INV) tz{k}f_run<T, PK>(task, zb, xb, lb, r, c, s, inst);",
+            f"        else tz{k}i_run<T, PK>(task, zb, xb, lb, r, c, s, inst);",
             "    }",
             "};"]) + "\n")
         write_if_changed(os.path.join(here, f"tz_gen_t{k}.cuh"), "\n".join(parts + TAIL) + "\n")

@@ -20,6 +20,142 @@
 #ifndef SNFFT_TZ_KIND
 #error "tz_kernels.cuh: define SNFFT_TZ_KIND (7 / 8 = Z kernel with that MB, 9 / 10 / 11 = T kernel of that level)"
 #endif
+#include "vec2.cuh"
+
+namespace snfft {
+namespace {
+
+// ---- short vectors of instances (T kernels) ------------------------------------------------------------------
+template <typename S, int NV>
+struct alignas(sizeof(S) * NV) TzVec {
+    S v[NV];
+    TzVec() = default;
+    __host__ __device__ __forceinline__ explicit TzVec(double x) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = (S)x;
+    }
+};
+// Elementwise arithmetic; fp32 vectors of even length go through the packed F2 operations of vec2.cuh (FFMA2 / FADD2 /
+// FMUL2: half the floating-point instructions of the straight-line code, same results).
+template <typename S, int NV>
+struct TzPairs {
+    static constexpr bool value = std::is_same<S, float>::value && NV % 2 == 0;
+};
+template <typename S, int NV>
+__host__ __device__ __forceinline__ F2 tz_pair(const TzVec<S, NV>& a, int i) {
+    F2 p;
+    p.x = (float)a.v[2 * i];
+    p.y = (float)a.v[2 * i + 1];
+    return p;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ void tz_set_pair(TzVec<S, NV>& a, int i, F2 p) {
+    a.v[2 * i] = (S)p.x;
+    a.v[2 * i + 1] = (S)p.y;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> sn_fma(const TzVec<S, NV>& a, const TzVec<S, NV>& b, const TzVec<S, NV>& c) {
+    TzVec<S, NV> r;
+    if constexpr (TzPairs<S, NV>::value) {
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) tz_set_pair(r, i, sn_fma(tz_pair(a, i), tz_pair(b, i), tz_pair(c, i)));
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r.v[i] = ::snfft::sn_fma(a.v[i], b.v[i], c.v[i]);
+    }
+    return r;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> operator*(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
+    TzVec<S, NV> r;
+    if constexpr (TzPairs<S, NV>::value) {
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) tz_set_pair(r, i, tz_pair(a, i) * tz_pair(b, i));
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] * b.v[i];
+    }
+    return r;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> operator+(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
+    TzVec<S, NV> r;
+    if constexpr (TzPairs<S, NV>::value) {
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) tz_set_pair(r, i, tz_pair(a, i) + tz_pair(b, i));
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] + b.v[i];
+    }
+    return r;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> operator-(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
+    TzVec<S, NV> r;
+    if constexpr (TzPairs<S, NV>::value) {
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) tz_set_pair(r, i, tz_pair(a, i) - tz_pair(b, i));
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] - b.v[i];
+    }
+    return r;
+}
+template <typename S, int NV>
+__host__ __device__ __forceinline__ TzVec<S, NV> operator-(const TzVec<S, NV>& a) {
+    TzVec<S, NV> r;
+    if constexpr (TzPairs<S, NV>::value) {
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) tz_set_pair(r, i, -tz_pair(a, i));
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r.v[i] = -a.v[i];
+    }
+    return r;
+}
+
+// Accessor of the level-k side of a T kernel for one parent lambda (outputs of the forward kernel, inputs of the inverse
+// one); rel = row * d_lambda + column of the element inside lambda, relative to the thread's (r, c).
+//   PK = false: the level array X_k, instance fastest: element e of lambda at (coef_off + e) * s + inst.
+//   PK = true (top level k = n only, NINST_n = B): the PUBLIC packed layout [lambda][B][d][d] (the (B, d, d) tensors
+//        sn_fft returns, fourier.py:291-295): element e of batch row b at coef_off * B + b d^2 + e.  The thread's NV
+//        instances are NV batch rows: NV scalar accesses d^2 apart; the warp tile of t_kernel (TZ_PK_CW columns x
+//        32 / TZ_PK_CW instance vectors) makes every such access a run of TZ_PK_CW consecutive elements per batch row.
+//        This replaces the separate pack / unpack pass over the coefficients (2 n! B sizeof of HBM traffic each).
+template <typename T, bool PK, bool CONST>
+struct TzAcc {
+    typename std::conditional<CONST, const T*, T*>::type p;
+    unsigned s;
+    __host__ __device__ __forceinline__ TzAcc(typename std::conditional<CONST, const T*, T*>::type lb, unsigned co, unsigned dl,
+                                              unsigned r, unsigned c, unsigned s_, unsigned inst)
+        : p(lb + ((size_t)co + r * dl + c) * s_ + inst), s(s_) {}
+    __host__ __device__ __forceinline__ void st(unsigned rel, const T& v) const { p[(size_t)rel * s] = v; }
+    __host__ __device__ __forceinline__ T ld(unsigned rel) const { return p[(size_t)rel * s]; }
+};
+template <typename S, int NV, bool CONST>
+struct TzAcc<TzVec<S, NV>, true, CONST> {
+    typedef TzVec<S, NV> T;
+    typename std::conditional<CONST, const S*, S*>::type p;
+    unsigned dd;
+    __host__ __device__ __forceinline__ TzAcc(typename std::conditional<CONST, const T*, T*>::type lb, unsigned co, unsigned dl,
+                                              unsigned r, unsigned c, unsigned s_, unsigned inst)
+        : p((typename std::conditional<CONST, const S*, S*>::type)lb + (size_t)co * NV * s_ + (size_t)(NV * inst) * (dl * dl) + r * dl + c),
+          dd(dl * dl) {}
+    __host__ __device__ __forceinline__ void st(unsigned rel, const T& v) const {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) p[rel + (size_t)i * dd] = v.v[i];
+    }
+    __host__ __device__ __forceinline__ T ld(unsigned rel) const {
+        T v;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v.v[i] = p[rel + (size_t)i * dd];
+        return v;
+    }
+};
+
+}  // namespace
+}  // namespace snfft
+
 #include "tz_gen_tab.cuh"
 #if SNFFT_TZ_KIND == 7
 #include "tz_gen_z7.cuh"
@@ -112,43 +248,6 @@ z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, int s_shift
 // The generated code is elementwise in the instance, so it runs unchanged on a short vector of instances:
 // 16-byte (8-byte) global transfers, NV times the bytes in flight per thread and 1/NV of the index arithmetic
 // (with scalar threads the kernel is latency bound: <= 10 loads of 4 bytes per thread at level 9).
-template <typename S, int NV>
-struct alignas(sizeof(S) * NV) TzVec {
-    S v[NV];
-    TzVec() = default;
-    __host__ __device__ __forceinline__ explicit TzVec(double x) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = (S)x;
-    }
-};
-template <typename S, int NV>
-__host__ __device__ __forceinline__ TzVec<S, NV> operator*(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
-    TzVec<S, NV> r;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] * b.v[i];
-    return r;
-}
-template <typename S, int NV>
-__host__ __device__ __forceinline__ TzVec<S, NV> operator+(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
-    TzVec<S, NV> r;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] + b.v[i];
-    return r;
-}
-template <typename S, int NV>
-__host__ __device__ __forceinline__ TzVec<S, NV> operator-(const TzVec<S, NV>& a, const TzVec<S, NV>& b) {
-    TzVec<S, NV> r;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) r.v[i] = a.v[i] - b.v[i];
-    return r;
-}
-template <typename S, int NV>
-__host__ __device__ __forceinline__ TzVec<S, NV> operator-(const TzVec<S, NV>& a) {
-    TzVec<S, NV> r;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) r.v[i] = -a.v[i];
-    return r;
-}
 constexpr int T_HINTS = 512;
 struct TTasks {
     int ntasks, hint_shift;
@@ -160,7 +259,20 @@ struct TTasks {
 // T = S (scalar threads) or TzVec<S, NV>; s = NINST_k / NV; s_shift = log2(s) when s is a power of two, else -1.
 // (A two-dimensional grid with the task in blockIdx.y and early exit of the tiles past a small task's end was
 // measured: 0.78 -> 0.97 ms at k = 9 -- 400 k empty CTAs are not free -- so the task is found by binary search.)
-template <typename T, int K, bool INV>
+// PK = true (top level, T = TzVec<S, NV>): the level-k side is the public packed layout (TzAcc).  A warp is then a tile
+// of TZ_PK_CW columns x 32 / TZ_PK_CW instance vectors of one row r: the instance-fastest side (Z, X_{k-1}) moves runs of
+// NV * 32 / TZ_PK_CW instances per column, the packed side runs of TZ_PK_CW columns per batch row; the tiles of one
+// (r, column tile) over the whole batch are adjacent (same CTA for B <= 8 * NV * 32 / TZ_PK_CW).
+#ifndef TZ_PK_CW
+#define TZ_PK_CW 16
+#endif
+__host__ __device__ __forceinline__ unsigned long long t_task_lanes(unsigned dal, unsigned dmu, unsigned s, bool pk) {
+    if (!pk) return (unsigned long long)dal * dmu * s;
+    constexpr unsigned IW = 32 / TZ_PK_CW;
+    return (unsigned long long)dal * ((dmu + TZ_PK_CW - 1) / TZ_PK_CW) * ((s + IW - 1) / IW) * 32ull;
+}
+
+template <typename T, int K, bool INV, bool PK>
 __global__ void __launch_bounds__(T_THREADS, 2)
 t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::conditional<INV, T*, const T*>::type xb,
          typename std::conditional<INV, const T*, T*>::type lb, unsigned s, int s_shift, const TTasks g) {
@@ -175,22 +287,35 @@ t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::co
     }
     const int task = lo;
     const unsigned dmu = TzDev<K>::dmu(task);
-    const unsigned long long qn = (unsigned long long)TzDev<K>::dal(task) * dmu * s;
+    const unsigned long long qn = t_task_lanes(TzDev<K>::dal(task), dmu, s, PK);
     const unsigned long long q = (unsigned long long)(b - g.blk0[task]) * T_THREADS + threadIdx.x;
     if (q >= qn) return;
-    unsigned rc, inst;
-    if (s_shift >= 0) {
-        rc = (unsigned)(q >> s_shift);
-        inst = (unsigned)q & (s - 1u);
-    } else if ((q >> 32) == 0) {
-        rc = (unsigned)q / s;
-        inst = (unsigned)q - rc * s;
+    unsigned r, c, inst;
+    if constexpr (PK) {
+        constexpr unsigned IW = 32 / TZ_PK_CW;
+        const unsigned nip = (s + IW - 1) / IW, nct = (dmu + TZ_PK_CW - 1) / TZ_PK_CW;
+        const unsigned lane = (unsigned)q & 31u, w = (unsigned)(q >> 5);
+        const unsigned rt = w / nip, ip = w - rt * nip;
+        r = rt / nct;
+        c = (rt - r * nct) * TZ_PK_CW + (lane % TZ_PK_CW);
+        inst = ip * IW + lane / TZ_PK_CW;
+        if (c >= dmu || inst >= s) return;
     } else {
-        rc = (unsigned)(q / s);
-        inst = (unsigned)(q - (unsigned long long)rc * s);
+        unsigned rc;
+        if (s_shift >= 0) {
+            rc = (unsigned)(q >> s_shift);
+            inst = (unsigned)q & (s - 1u);
+        } else if ((q >> 32) == 0) {
+            rc = (unsigned)q / s;
+            inst = (unsigned)q - rc * s;
+        } else {
+            rc = (unsigned)(q / s);
+            inst = (unsigned)(q - (unsigned long long)rc * s);
+        }
+        r = rc / dmu;
+        c = rc - r * dmu;
     }
-    const unsigned r = rc / dmu, c = rc - r * dmu;
-    TzDev<K>::template run<T, INV>(task, zb + inst, xb + inst, lb + inst, r, c, s);
+    TzDev<K>::template run<T, INV, PK>(task, zb + inst, xb + inst, lb, r, c, s, inst);
 }
 #endif
 

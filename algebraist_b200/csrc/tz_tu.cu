@@ -146,9 +146,33 @@ extern "C" int TZ_ZNAME(int k, const void* src, void* dst, long long ninst, cuda
     // 32-bit strides: row stride d_mu k NINST of X_{k-1} (d_mu <= 216 at k = 10, <= 768 at k = 11)
     if (ninst <= 0 || (unsigned long long)ninst * (k == 11 ? 768ull : 216ull) * (unsigned long long)k >= (1ull << 32))
         return (int)cudaErrorInvalidValue;
+    bool v2 = false;
+    int s_shift2 = -1;
+#if !SNFFT_TZ_F64
+    // fp32: two adjacent instances per thread as one F2 (vec2.cuh) when the instance count and the buffers allow it;
+    // SNFFT_TZ_ZV2=0 keeps the scalar threads (bit-identical results)
+    static const bool v2_on = [] {
+        const char* e = std::getenv("SNFFT_TZ_ZV2");
+        return !e || std::atoi(e) != 0;
+    }();
+    static const int chunk2 = [] {
+        const char* e = std::getenv("SNFFT_TZ_CHUNK2");
+        return e ? std::atoi(e) : (SNFFT_TZ_INV ? 37 : 74);
+    }();
+    v2 = v2_on && ninst % 2 == 0 && ((uintptr_t)src | (uintptr_t)dst) % sizeof(F2) == 0;
+    if (v2) {
+        ninst /= 2;
+        if ((ninst & (ninst - 1)) == 0)
+            for (s_shift2 = 0; (1ll << s_shift2) < ninst; ++s_shift2) {
+            }
+    }
+    const int chunk_used = v2 ? chunk2 : chunk;
+#else
+    const int chunk_used = chunk;
+#endif
     ZGroups g;
     g.ngroups = I::ngroups;
-    g.chunk = chunk < 1 ? 1 : chunk;
+    g.chunk = chunk_used < 1 ? 1 : chunk_used;
     g.k = k;
     unsigned long long blk = 0;
     for (int i = 0; i < I::ngroups; ++i) {
@@ -163,6 +187,14 @@ extern "C" int TZ_ZNAME(int k, const void* src, void* dst, long long ninst, cuda
     if (blk > 0x7fffffffull) return (int)cudaErrorInvalidValue;
     if (blk == 0) return 0;
     dim3 grid((unsigned)blk, 1, 1), block(Z_THREADS, 1, 1);
+#if !SNFFT_TZ_F64
+    if (v2) {
+        auto kfn2 = z_kernel<F2, SNFFT_TZ_INV != 0>;
+        SNFFT_LAUNCH(kfn2, grid, block, 0, st, (const F2*)src, (F2*)dst, (unsigned)ninst, s_shift2, g, (const ZSeg*)d->segs,
+                     (const unsigned*)d->unit2seg);
+        return (int)cudaGetLastError();
+    }
+#endif
     auto kfn = z_kernel<tz_t, SNFFT_TZ_INV != 0>;
     int s_shift = -1;
     if ((ninst & (ninst - 1)) == 0)
