@@ -38,6 +38,10 @@ COL_COMBOS = [(k, f64, inv) for k in (6, 7, 8) for f64 in (0, 1) for inv in (0, 
 # different tasks per SM): forward k = 9 3.36 -> 2.30 ms, fp64 5.6 -> 3.7 ms; level 7 is faster with 128.
 COL_THREADS = {(8, 0): 640, (8, 1): 384}
 
+if os.environ.get("SNFFT_TZ_PK_TUNE"):          # tuning build: all three warp-tile widths of the packed T kernels (SNFFT_TZ_PK_CW picks)
+    TZ_EXTRA = ["-DSNFFT_TZ_PK_TUNE=1"]
+else:
+    TZ_EXTRA = []
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
@@ -48,7 +52,7 @@ def units():
            f"-DSNFFT_COL_THREADS={COL_THREADS.get((k, f64), 128)}"], col_deps(k))
          for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
     u += [(os.path.join(OBJ, f"tz_{kind}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "tz_tu.cu"),
-           [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"], tz_deps(kind))
+           [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"] + TZ_EXTRA, tz_deps(kind))
           for kind, f64, inv in TZ_COMBOS]
     u.insert(0, (os.path.join(OBJ, "snfft.o"), os.path.join(CSRC, "snfft.cu"), [], MAIN_DEPS))
     u.append((os.path.join(OBJ, "plan.o"), os.path.join(CSRC, "plan.cpp"), [], PLAN_DEPS))

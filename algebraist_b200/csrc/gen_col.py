@@ -36,6 +36,17 @@ CHILD_MAJOR_MAX = 6       # levels whose tasks keep a whole child column in regi
 # to 4 cosets = 64 sums; level 8 spills beyond 2)
 PREFETCH = os.environ.get("SNFFT_GEN_PREFETCH", "1") != "0"      # issue a chain's / block's loads one step ahead of the arithmetic
 INV_COSETS_PER_TASK = {7: int(os.environ.get("SNFFT_GEN_INV_COSETS_7", "4")), 8: int(os.environ.get("SNFFT_GEN_INV_COSETS_8", "2"))}
+# ... and at most this many running sums per inverse task (cosets x rows of mu): the two d = 35 shapes of level 7 with two
+# cosets (70 sums) spilled 0.5-1.3 KB per thread in the six tasks that do most of level 8's work (profiles r02u: 2.2 GB
+# written for 1.86 GB of output); they run one coset per task
+INV_SUMS_CAP = {7: int(os.environ.get("SNFFT_GEN_INV_SUMS_7", "64")), 8: int(os.environ.get("SNFFT_GEN_INV_SUMS_8", "48"))}
+
+
+def inv_cosets(k, d):
+    """Adjacent cosets per inverse task of level k for a child shape of dimension d."""
+    return max(1, min(INV_COSETS_PER_TASK[k], INV_SUMS_CAP[k] // d))
+
+
 SPLIT_FWD = {}            # forward-only levels generated in parts (level 9, until the top / bottom kernels of gen_tz.py took it over)
 # forward tasks: rows of output a task owns at most (level 8: adjacent child blocks are merged up to this many rows,
 # so that small blocks share their loads; level 7: several parents of one child shape per task, as many as fit this
@@ -437,7 +448,7 @@ def gen_level(k, inverse, only=None):
             # one task per (row set, coset i): a function that ran all k chains would keep the addresses of the rows of
             # F_lambda (the same in every chain) live throughout and spill
             for rows in row_sets(7, mu):                 # all rows of mu: the block of mu in F_lambda is then read once
-                for grp in coset_groups(k, INV_COSETS_PER_TASK[k]):
+                for grp in coset_groups(k, inv_cosets(k, dm)):
                     em = ScaledEmitter()
 
                     def load(lam, t, bo, em=em):

@@ -36,7 +36,7 @@ import math
 import os
 
 from gen_base import ScaledEmitter, boffs, children, coef_off, dim, partitions
-from gen_col import (FWD_ROWS_CAP, INV_COSETS_PER_TASK, coset_groups, forward_task, forward_task_multi, inverse_task_multi,
+from gen_col import (FWD_ROWS_CAP, coset_groups, inv_cosets, forward_task, forward_task_multi, inverse_task_multi,
                      need_chain, parent_groups, row_sets, sweep_need, value_expr, write_if_changed)
 
 LEVEL_MB = {9: 7, 10: 7, 11: 8}        # level k -> bottom level MB (the Z kernel runs level-MB column operators)
@@ -128,7 +128,7 @@ def gen_z(MB, inverse):
                 cases.append(f"        case {task}: {tag}_{task}<T>(in, out, rs, s, zs); break;")
                 task += 1
         else:
-            for grp in coset_groups(MB, INV_COSETS_PER_TASK[MB]):
+            for grp in coset_groups(MB, inv_cosets(MB, dz)):
                 em = ScaledEmitter()
 
                 def load(alpha, t, bo, em=em, zeta=zeta):

@@ -672,7 +672,10 @@ extern "C" {
     int snfft_tz_z8_prepare_##dt##_##dir(int);                                                 \
     int snfft_tz_t9_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);                \
     int snfft_tz_t10_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);               \
-    int snfft_tz_t11_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);
+    int snfft_tz_t11_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);               \
+    int snfft_tz_tpk9_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);              \
+    int snfft_tz_tpk10_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);             \
+    int snfft_tz_tpk11_##dt##_##dir(void*, void*, void*, long long, cudaStream_t);
 SNFFT_TZ_DECL(f32, fwd) SNFFT_TZ_DECL(f32, inv) SNFFT_TZ_DECL(f64, fwd) SNFFT_TZ_DECL(f64, inv)
 #undef SNFFT_TZ_DECL
 }
@@ -702,11 +705,25 @@ static int tz_prepare(int dtype, int k, bool fwd, bool inv) {
     return SNFFT_OK;
 }
 
+// The top level's T kernel can read / write the public packed coefficients directly (tz_tu.cu: snfft_tz_tpk*): no
+// separate pack / unpack pass.  Needs full instance vectors; SNFFT_TZ_PACK=0 keeps the two-pass route.
+template <typename T>
+static bool tz_pack_ok(const snfft_plan* p, int k, long long B, const void* level_buf, const void* z, const void* packed) {
+    static const bool on = [] {
+        const char* e = std::getenv("SNFFT_TZ_PACK");
+        return !e || std::atoi(e) != 0;
+    }();
+    const long long nv = 16 / (long long)sizeof(T);
+    return on && k == p->n && B % nv == 0 && ((uintptr_t)level_buf | (uintptr_t)z) % 16 == 0 && (uintptr_t)packed % sizeof(T) == 0;
+}
+
 // One level step through the top / bottom kernels.  forward: in = X_{k-1}, out = X_k; inverse: in = X_k,
-// out = X_{k-1}; z = the third workspace buffer (MB/k of a level array is used).
-// Profile records: kernel_class -4 = Z kernel, -5 = T kernel.
+// out = X_{k-1}; z = the third workspace buffer (MB/k of a level array is used).  packed (k = n, tz_pack_ok): the
+// level-n side (forward: out, inverse: in) is the public packed layout [lambda][B][d][d].
+// Profile records: kernel_class -4 = Z kernel, -5 = T kernel (-7 = T kernel on the packed layout).
 template <typename T, bool INVERSE>
-static int run_tz_level(const snfft_plan* p, int k, const void* in, void* out, void* z, long long B, cudaStream_t st) {
+static int run_tz_level(const snfft_plan* p, int k, const void* in, void* out, void* z, long long B, cudaStream_t st,
+                        bool packed = false) {
     const long long ninst = B * (p->host.factorial[p->n] / p->host.factorial[k]);
     const long long fk = p->host.factorial[k];
     int rc;
@@ -721,13 +738,16 @@ static int run_tz_level(const snfft_plan* p, int k, const void* in, void* out, v
         zfn = mb == 7 ? (F32 ? snfft_tz_z7_f32_fwd : snfft_tz_z7_f64_fwd) : (F32 ? snfft_tz_z8_f32_fwd : snfft_tz_z8_f64_fwd);
         tfn = k == 9 ? (F32 ? snfft_tz_t9_f32_fwd : snfft_tz_t9_f64_fwd)
                      : (k == 10 ? (F32 ? snfft_tz_t10_f32_fwd : snfft_tz_t10_f64_fwd) : (F32 ? snfft_tz_t11_f32_fwd : snfft_tz_t11_f64_fwd));
+        if (packed)
+            tfn = k == 9 ? (F32 ? snfft_tz_tpk9_f32_fwd : snfft_tz_tpk9_f64_fwd)
+                         : (k == 10 ? (F32 ? snfft_tz_tpk10_f32_fwd : snfft_tz_tpk10_f64_fwd) : (F32 ? snfft_tz_tpk11_f32_fwd : snfft_tz_tpk11_f64_fwd));
         {
             ProfScope prof(p, st, 0, k, -4, fk * mb / k);
             rc = zfn(k, in, z, ninst, st);
             g_launches.fetch_add(1);
             if (rc) return fail(rc);
         }
-        ProfScope prof(p, st, 0, k, -5, fk);
+        ProfScope prof(p, st, 0, k, packed ? -7 : -5, fk);
         rc = tfn(z, (void*)in, out, ninst, st);
         g_launches.fetch_add(1);
         if (rc) return fail(rc);
@@ -735,8 +755,11 @@ static int run_tz_level(const snfft_plan* p, int k, const void* in, void* out, v
         zfn = mb == 7 ? (F32 ? snfft_tz_z7_f32_inv : snfft_tz_z7_f64_inv) : (F32 ? snfft_tz_z8_f32_inv : snfft_tz_z8_f64_inv);
         tfn = k == 9 ? (F32 ? snfft_tz_t9_f32_inv : snfft_tz_t9_f64_inv)
                      : (k == 10 ? (F32 ? snfft_tz_t10_f32_inv : snfft_tz_t10_f64_inv) : (F32 ? snfft_tz_t11_f32_inv : snfft_tz_t11_f64_inv));
+        if (packed)
+            tfn = k == 9 ? (F32 ? snfft_tz_tpk9_f32_inv : snfft_tz_tpk9_f64_inv)
+                         : (k == 10 ? (F32 ? snfft_tz_tpk10_f32_inv : snfft_tz_tpk10_f64_inv) : (F32 ? snfft_tz_tpk11_f32_inv : snfft_tz_tpk11_f64_inv));
         {
-            ProfScope prof(p, st, 1, k, -5, fk);
+            ProfScope prof(p, st, 1, k, packed ? -7 : -5, fk);
             rc = tfn(z, out, (void*)in, ninst, st);
             g_launches.fetch_add(1);
             if (rc) return fail(rc);
@@ -752,13 +775,20 @@ static int run_tz_level(const snfft_plan* p, int k, const void* in, void* out, v
 static IndexArgs make_index_args(int n);
 
 // level steps k_first .. n of the forward pipeline: cur = X_{k_first - 1} on entry, X_n on return
+// F_packed != nullptr: the caller wants the packed coefficients there; when the top level runs the top / bottom kernels
+// its T kernel writes them directly and *packed_done is set (otherwise the caller packs X_n itself).
 template <typename T>
 static int forward_level_range(const snfft_plan* p, int k_first, void*& cur, void*& nxt, void* zbuf, long long B, cudaStream_t st,
-                               int k_stop = -1) {
+                               int k_stop = -1, void* F_packed = nullptr, bool* packed_done = nullptr) {
     const int base = g_no_base.load();
     const int k_end = k_stop < 0 ? p->n : k_stop - 1;
     for (int k = k_first; k <= k_end; ++k) {
         int rc;
+        if (base == 0 && p->lev[k].tz_fwd && F_packed && packed_done && tz_pack_ok<T>(p, k, B, cur, zbuf, F_packed)) {
+            if ((rc = run_tz_level<T, false>(p, k, cur, F_packed, zbuf, B, st, true))) return rc;
+            *packed_done = true;
+            return SNFFT_OK;
+        }
         if (base == 0 && p->lev[k].tz_fwd) rc = run_tz_level<T, false>(p, k, cur, nxt, zbuf, B, st);
         else if (base == 0 && p->lev[k].col_fwd) rc = run_col_level<T, false>(p, k, cur, nxt, B, st);
         else rc = run_fwd_level<T>(p, k, cur, nxt, B, st);
@@ -771,7 +801,8 @@ static int forward_level_range(const snfft_plan* p, int k_first, void*& cur, voi
 // levels 1..n of the forward pipeline; *result points at X_n (instance fastest) inside the workspace
 template <typename T>
 static int forward_levels(const snfft_plan* p, const void* f, long long B, void* ws, cudaStream_t st, void** result,
-                          int k_stop = -1, void** other = nullptr) {          // k_stop: stop before that level step
+                          int k_stop = -1, void** other = nullptr,          // k_stop: stop before that level step
+                          void* F_packed = nullptr, bool* packed_done = nullptr) {
     const size_t half = (size_t)B * p->host.factorial[p->n] * sizeof(T);
     void* cur = ws;
     void* nxt = (char*)ws + half;
@@ -785,7 +816,7 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
         std::swap(cur, nxt);
         k_first = 6;
     }
-    if ((rc = forward_level_range<T>(p, k_first, cur, nxt, zbuf, B, st, k_stop))) return rc;
+    if ((rc = forward_level_range<T>(p, k_first, cur, nxt, zbuf, B, st, k_stop, F_packed, packed_done))) return rc;
     *result = cur;
     if (other) *other = nxt;
     return SNFFT_OK;
@@ -794,8 +825,10 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
 template <typename T>
 static int forward_impl(const snfft_plan* p, const void* f, long long B, void* F, void* ws, cudaStream_t st) {
     void* xn = nullptr;
-    const int rc = forward_levels<T>(p, f, B, ws, st, &xn);
+    bool packed = false;
+    const int rc = forward_levels<T>(p, f, B, ws, st, &xn, -1, nullptr, F, &packed);
     if (rc) return rc;
+    if (packed) return SNFFT_OK;
     return run_pack<T, true>(p, xn, F, B, st);
 }
 
@@ -886,7 +919,9 @@ static int forward_cosets2_impl(const snfft_plan* pn, const snfft_plan* pm, cons
         g_launches.fetch_add(1);
         SNFFT_CUDA(cudaGetLastError());
     }
-    if ((rc = forward_level_range<T>(pn, n - 1, cur, nxt, zbuf, B, st))) return rc;
+    bool packed = false;
+    if ((rc = forward_level_range<T>(pn, n - 1, cur, nxt, zbuf, B, st, -1, F, &packed))) return rc;
+    if (packed) return SNFFT_OK;
     return run_pack<T, true>(pn, cur, F, B, st);
 }
 
@@ -900,6 +935,11 @@ static int inverse_impl(const snfft_plan* p, const void* F, long long B, void* f
     void* bufs[2] = {ws, (char*)ws + half};
     void* zbuf = (char*)ws + 2 * half;
     int rc;
+    if (g_no_base.load() == 0 && p->lev[p->n].tz_inv && tz_pack_ok<T>(p, p->n, B, bufs[1], zbuf, F)) {
+        // the top level's T kernel reads the packed coefficients itself
+        if ((rc = run_tz_level<T, true>(p, p->n, F, bufs[1], zbuf, B, st, true))) return rc;
+        return inverse_tail<T>(p, p->n - 1, bufs[1], bufs, 0, zbuf, B, f, st);
+    }
     if ((rc = run_pack<T, false>(p, F, bufs[0], B, st))) return rc;
     return inverse_tail<T>(p, p->n, bufs[0], bufs, 1, zbuf, B, f, st);
 }

@@ -22,8 +22,7 @@
 #endif
 #include "vec2.cuh"
 
-namespace snfft {
-namespace {
+namespace snfft {       // not the anonymous namespace: sn_fma must overload with vec2.cuh's for the generated code
 
 // ---- short vectors of instances (T kernels) ------------------------------------------------------------------
 template <typename S, int NV>
@@ -153,7 +152,6 @@ struct TzAcc<TzVec<S, NV>, true, CONST> {
     }
 };
 
-}  // namespace
 }  // namespace snfft
 
 #include "tz_gen_tab.cuh"
@@ -260,19 +258,17 @@ struct TTasks {
 // (A two-dimensional grid with the task in blockIdx.y and early exit of the tiles past a small task's end was
 // measured: 0.78 -> 0.97 ms at k = 9 -- 400 k empty CTAs are not free -- so the task is found by binary search.)
 // PK = true (top level, T = TzVec<S, NV>): the level-k side is the public packed layout (TzAcc).  A warp is then a tile
-// of TZ_PK_CW columns x 32 / TZ_PK_CW instance vectors of one row r: the instance-fastest side (Z, X_{k-1}) moves runs of
+// of TZ_PK_CW (template parameter) columns x 32 / TZ_PK_CW instance vectors of one row r: the instance-fastest side (Z, X_{k-1}) moves runs of
 // NV * 32 / TZ_PK_CW instances per column, the packed side runs of TZ_PK_CW columns per batch row; the tiles of one
 // (r, column tile) over the whole batch are adjacent (same CTA for B <= 8 * NV * 32 / TZ_PK_CW).
-#ifndef TZ_PK_CW
-#define TZ_PK_CW 16
-#endif
-__host__ __device__ __forceinline__ unsigned long long t_task_lanes(unsigned dal, unsigned dmu, unsigned s, bool pk) {
-    if (!pk) return (unsigned long long)dal * dmu * s;
-    constexpr unsigned IW = 32 / TZ_PK_CW;
-    return (unsigned long long)dal * ((dmu + TZ_PK_CW - 1) / TZ_PK_CW) * ((s + IW - 1) / IW) * 32ull;
+// cw = 0: not packed
+__host__ __device__ __forceinline__ unsigned long long t_task_lanes(unsigned dal, unsigned dmu, unsigned s, unsigned cw) {
+    if (cw == 0) return (unsigned long long)dal * dmu * s;
+    const unsigned iw = 32 / cw;
+    return (unsigned long long)dal * ((dmu + cw - 1) / cw) * ((s + iw - 1) / iw) * 32ull;
 }
 
-template <typename T, int K, bool INV, bool PK>
+template <typename T, int K, bool INV, bool PK, int TZ_PK_CW = 16>
 __global__ void __launch_bounds__(T_THREADS, 2)
 t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::conditional<INV, T*, const T*>::type xb,
          typename std::conditional<INV, const T*, T*>::type lb, unsigned s, int s_shift, const TTasks g) {
@@ -287,7 +283,7 @@ t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::co
     }
     const int task = lo;
     const unsigned dmu = TzDev<K>::dmu(task);
-    const unsigned long long qn = t_task_lanes(TzDev<K>::dal(task), dmu, s, PK);
+    const unsigned long long qn = t_task_lanes(TzDev<K>::dal(task), dmu, s, PK ? TZ_PK_CW : 0);
     const unsigned long long q = (unsigned long long)(b - g.blk0[task]) * T_THREADS + threadIdx.x;
     if (q >= qn) return;
     unsigned r, c, inst;

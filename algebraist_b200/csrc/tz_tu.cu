@@ -8,6 +8,7 @@
 //   int snfft_tz_z<MB>_prepare_<f32|f64>_<fwd|inv>(int k)    uploads the level's segment tables to the current device
 //   int snfft_tz_t<k>_<f32|f64>_<fwd|inv>(void* z, void* x, void* xk, long long ninst, stream)
 //        forward: reads z, x (= X_{k-1}), writes xk (= X_k);  inverse: reads xk, writes z and the cosets i >= 7 of x
+//   int snfft_tz_tpk<k>_<f32|f64>_<fwd|inv>(...)   the same with xk = the packed coefficients [lambda][B][d][d] (k = n)
 #ifdef SNFFT_HOST_EMU
 #include "cuda_emu.h"
 #else
@@ -38,6 +39,15 @@ typedef float tz_t;
 #endif
 #ifndef TZ_VEC_DEFAULT
 #define TZ_VEC_DEFAULT 4
+#endif
+#ifndef TZ_PK_CW_DEFAULT
+// measured at S_10, B = 128, fp32 (profiles r02v): forward (scalar STORES to the packed side) 1.38 / 1.21 / 1.11 ms with
+// 8 / 16 / 32 columns per warp tile, inverse (scalar LOADS from it) 1.03 / 0.97 / 1.19 ms
+#if SNFFT_TZ_INV
+#define TZ_PK_CW_DEFAULT 16
+#else
+#define TZ_PK_CW_DEFAULT 32
+#endif
 #endif
 #define TZ_CAT3_(a, b, c) a##b##_##c
 #define TZ_CAT3(a, b, c) TZ_CAT3_(a, b, c)
@@ -210,8 +220,15 @@ extern "C" int TZ_ZNAME(int k, const void* src, void* dst, long long ninst, cuda
 #define TZ_TNAME_(k, dt, dir) snfft_tz_t##k##_##dt##_##dir
 #define TZ_TNAME__(k, dt, dir) TZ_TNAME_(k, dt, dir)
 #define TZ_TNAME TZ_TNAME__(SNFFT_TZ_KIND, TZ_DT, TZ_DIR)
+#define TZ_TPKNAME_(k, dt, dir) snfft_tz_tpk##k##_##dt##_##dir
+#define TZ_TPKNAME__(k, dt, dir) TZ_TPKNAME_(k, dt, dir)
+#define TZ_TPKNAME TZ_TPKNAME__(SNFFT_TZ_KIND, TZ_DT, TZ_DIR)
 
-extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_t st) {
+// pk != 0 (top level only, NINST = B): xk is the public packed coefficient array [lambda][B][d][d] instead of the level
+// array X_k -- the pack (forward) / unpack (inverse) pass is fused into this kernel (TzAcc, tz_kernels.cuh).  Needs the
+// widest instance vector (B % 4 == 0 for fp32, B % 2 == 0 for fp64, 16-byte aligned z / x); returns
+// cudaErrorInvalidValue otherwise (snfft.cu: tz_pack_ok decides before the call).
+static int tz_t_launch(void* z, void* x, void* xk, long long ninst, int pk, cudaStream_t st) {
     using namespace snfft;
     using L = TzLevel<SNFFT_TZ_KIND>;
     static_assert(L::ntasks <= T_MAXTASKS, "too many T tasks");
@@ -221,16 +238,25 @@ extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_
         const char* e = std::getenv("SNFFT_TZ_VEC");
         return e ? std::atoi(e) : TZ_VEC_DEFAULT;
     }();
-    int nv = 16 / (int)sizeof(tz_t);
+    constexpr int nv_max = 16 / (int)sizeof(tz_t);
+    int nv = nv_max;
     if (nv > vec_cap) nv = vec_cap < 1 ? 1 : vec_cap;
-    while (nv > 1 && (ninst % nv != 0 || ((uintptr_t)z | (uintptr_t)x | (uintptr_t)xk) % (sizeof(tz_t) * nv) != 0)) nv >>= 1;
+    const uintptr_t align_bits = pk ? ((uintptr_t)z | (uintptr_t)x) : ((uintptr_t)z | (uintptr_t)x | (uintptr_t)xk);
+    while (nv > 1 && (ninst % nv != 0 || align_bits % (sizeof(tz_t) * nv) != 0)) nv >>= 1;
+    if (pk && (nv != nv_max || (uintptr_t)xk % sizeof(tz_t) != 0)) return (int)cudaErrorInvalidValue;
     ninst /= nv;
+    // columns per warp tile of the packed kernels (tz_kernels.cuh): SNFFT_TZ_PK_CW = 8 | 16 | 32 (tuning switch)
+    static const int pk_cw = [] {
+        const char* e = std::getenv("SNFFT_TZ_PK_CW");
+        const int v = e ? std::atoi(e) : TZ_PK_CW_DEFAULT;
+        return v == 8 || v == 32 ? v : 16;
+    }();
     TTasks g;
     g.ntasks = L::ntasks;
     unsigned long long blk = 0;
     for (int t = 0; t < L::ntasks; ++t) {
         g.blk0[t] = (unsigned)blk;
-        const unsigned long long q = (unsigned long long)L::t_dal()[t] * L::t_dmu()[t] * (unsigned long long)ninst;
+        const unsigned long long q = t_task_lanes((unsigned)L::t_dal()[t], (unsigned)L::t_dmu()[t], (unsigned)ninst, pk ? (unsigned)pk_cw : 0u);
         blk += (q + T_THREADS - 1) / T_THREADS;
     }
     for (int t = L::ntasks; t <= T_MAXTASKS; ++t) g.blk0[t] = (unsigned)blk;
@@ -248,31 +274,39 @@ extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_
         }
     dim3 grid((unsigned)blk, 1, 1), block(T_THREADS, 1, 1);
 #if SNFFT_TZ_INV
-#define TZ_T_LAUNCH(VT)                                                                                   \
+#define TZ_T_LAUNCH(VT, PK, CW)                                                                           \
     {                                                                                                     \
-        auto kfn = t_kernel<VT, SNFFT_TZ_KIND, true>;                                                     \
+        auto kfn = t_kernel<VT, SNFFT_TZ_KIND, true, PK, CW>;                                             \
         SNFFT_LAUNCH(kfn, grid, block, 0, st, (VT*)z, (VT*)x, (const VT*)xk, (unsigned)ninst, s_shift, g);         \
     }
 #else
-#define TZ_T_LAUNCH(VT)                                                                                   \
+#define TZ_T_LAUNCH(VT, PK, CW)                                                                           \
     {                                                                                                     \
-        auto kfn = t_kernel<VT, SNFFT_TZ_KIND, false>;                                                    \
+        auto kfn = t_kernel<VT, SNFFT_TZ_KIND, false, PK, CW>;                                            \
         SNFFT_LAUNCH(kfn, grid, block, 0, st, (const VT*)z, (const VT*)x, (VT*)xk, (unsigned)ninst, s_shift, g);   \
     }
 #endif
-    if (nv == 4) {
-#if !SNFFT_TZ_F64
-        using V4 = TzVec<tz_t, 4>;
-        TZ_T_LAUNCH(V4)
+    using VMAX = TzVec<tz_t, nv_max>;
+    if (pk) {
+#ifdef SNFFT_TZ_PK_TUNE
+        if (pk_cw == 8) TZ_T_LAUNCH(VMAX, true, 8)
+        else if (pk_cw == 32) TZ_T_LAUNCH(VMAX, true, 32)
+        else
 #endif
+        TZ_T_LAUNCH(VMAX, true, TZ_PK_CW_DEFAULT)
+    } else if (nv == nv_max) {
+        TZ_T_LAUNCH(VMAX, false, 16)
     } else if (nv == 2) {
         using V2 = TzVec<tz_t, 2>;
-        TZ_T_LAUNCH(V2)
+        TZ_T_LAUNCH(V2, false, 16)
     } else {
-        TZ_T_LAUNCH(tz_t)
+        TZ_T_LAUNCH(tz_t, false, 16)
     }
 #undef TZ_T_LAUNCH
     return (int)cudaGetLastError();
 }
+
+extern "C" int TZ_TNAME(void* z, void* x, void* xk, long long ninst, cudaStream_t st) { return tz_t_launch(z, x, xk, ninst, 0, st); }
+extern "C" int TZ_TPKNAME(void* z, void* x, void* xk, long long ninst, cudaStream_t st) { return tz_t_launch(z, x, xk, ninst, 1, st); }
 
 #endif

@@ -243,7 +243,9 @@ int snfft_dense_rep(snfft_plan_t* plan, int part, void* out, void* stream);
  *   kernel_class: 0..5 table-driven sweep-kernel classes, -1 generated base kernel / scalar data movement,
  *         -2 vectorised data movement, -3 register column kernels (levels 6..8: col_kernels.cuh),
  *         -4 / -5 the Z / T kernel of a top / bottom level step (levels 9..11: tz_kernels.cuh),
- *         -6 small-batch gather / scatter and the B = 1 pack copy
+ *         -6 small-batch gather / scatter and the B = 1 pack copy,
+ *         -7 the T kernel of the TOP level reading / writing the packed coefficients itself (no pack / unpack launch:
+ *            batches with full instance vectors, B % 4 == 0 fp32, B % 2 == 0 fp64)
  *   elems_per_instance: coefficients the launch produces per function
  *     (its share of k!; the launch reads as many; the Z kernel: MB/k of k!), so its algorithmic traffic
  *     is 2 * elems_per_instance * NINST_level * sizeof(dtype) bytes.

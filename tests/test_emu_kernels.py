@@ -195,10 +195,12 @@ def test_kernel_families_vs_oracle(emu, n, mode, base, dt):
         emu.snfft_plan_destroy(plan)
 
 
-def test_level9_top_bottom_kernels_vs_oracle(emu):
+@pytest.mark.parametrize("B", [1, 2])
+def test_level9_top_bottom_kernels_vs_oracle(emu, B):
     """n = 9 in automatic mode: the level step k = 9 runs the top / bottom kernels (tz_kernels.cuh: level-7 column
-    operators on pieces of the inputs, then the two top sweeps) in both directions; against the oracle on one function."""
-    n, B = 9, 1
+    operators on pieces of the inputs, then the two top sweeps) in both directions; against the oracle.  B = 2: full
+    instance vectors, so the T kernel of the top level reads / writes the packed coefficients itself (no pack / unpack pass)."""
+    n = 9
     rng = np.random.default_rng(9)
     f = rng.standard_normal((B, math.factorial(n)))
     abi = CAbi(emu)

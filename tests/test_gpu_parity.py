@@ -59,9 +59,11 @@ def test_forward_inverse_vs_reference_golden(A, n, dt):
         assert rel_err(inv.cpu().numpy(), g[f"n{n}_{dt}_ift"]) < TOL[dt]
 
 
-@pytest.mark.parametrize("n,B", [(9, 3), (10, 2)])
+@pytest.mark.parametrize("n,B", [(9, 3), (10, 2), (9, 4), (10, 4)])
 @pytest.mark.parametrize("dt", ["f32", "f64"])
 def test_vs_oracle_large_n(A, n, B, dt):
+    """B = 4 (fp64: also B = 2): full instance vectors, so the top level's T kernel reads / writes the packed
+    coefficients itself; B = 3 (fp32: also 2): the separate pack / unpack kernels."""
     rng = np.random.default_rng(100 * n + B)
     f = rng.standard_normal((B, math.factorial(n)))
     ref = O.sn_fft_packed(f, n)

@@ -52,7 +52,7 @@ def main():
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
         name = name.replace("void ", "").replace("(LevelArgs<T1>)", "")
-        line = [name[:60], r[col["Grid Size"]], r[col["Block Size"]]]
+        line = [name[:90], r[col["Grid Size"]], r[col["Block Size"]]]
         for k, _ in KEYS:
             if k in col:
                 v = r[col[k]]

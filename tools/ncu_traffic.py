@@ -6,6 +6,7 @@ kernel family is matched to the bench name by its template arguments and grid.
     python tools/ncu_traffic.py summary.csv batch dtype out.json [n]
 """
 import csv
+import re
 import json
 import sys
 
@@ -27,21 +28,25 @@ def main():
     fam = {"inv_level_kernel<float, 4, 4, 64": "inv_level_k10_c3", "fwd_level_kernel<float, 4, 4, 64": "fwd_level_k10_c3",
            "inv_level_kernel<double, 2, 4, 64": "inv_level_k10_c3", "fwd_level_kernel<double, 2, 4, 64": "fwd_level_k10_c3"}
     # column kernels (col_kernels.cuh): one launch per level and direction
-    for t in ("float", "double"):
-        for k in (6, 7, 8):
-            fam[f"col_kernel<{t}, {k}, 0>"] = f"fwd_level_k{k}_c-3"
-            fam[f"col_kernel<{t}, {k}, 1>"] = f"inv_level_k{k}_c-3"
+    # (names as ncu prints them: col_kernel<float, 8, 0, 640>, col_kernel<F2, 8, 0, 384> -- the F2 instantiation runs two
+    # fp32 instances per thread)
+    cpat = re.compile(r"col_kernel<(?:snfft::)?(float|double|F2), (?:\(int\))?(\d+), (?:\(bool\))?([01])")
     # top / bottom kernels: the T kernel names its level and direction; the Z kernel (level-7 operators) runs for
     # k = 9 and 10 in a fixed order inside one forward + inverse: forward 9, forward 10, inverse 10, inverse 9
-    import re
-    tpat = re.compile(r"t_kernel<.*?(float|double)(?:, \d)?>?, (\d+), ([01])>")
+    # t_kernel<TzVec<float, 4>, 10, 0, 1>: level, direction, packed (the top level's kernel on the public layout: class -7)
+    tpat = re.compile(r"t_kernel<.*?(float|double)(?:, (?:\(int\))?\d)?>?, (?:\(int\))?(\d+), (?:\(bool\))?([01])(?:, (?:\(bool\))?([01]))?")
     zorder = {"0": ["fwd_level_k9_c-4", "fwd_level_k10_c-4"], "1": ["inv_level_k10_c-4", "inv_level_k9_c-4"]}
     zseen = {"0": 0, "1": 0}
     best = {}
     for r in rows[1:]:
         m = tpat.search(r[ki])
         if m:
-            name = f"{'inv' if m.group(3) == '1' else 'fwd'}_level_k{m.group(2)}_c-5"
+            name = f"{'inv' if m.group(3) == '1' else 'fwd'}_level_k{m.group(2)}_c{'-7' if m.group(4) == '1' else '-5'}"
+            best[name] = (float(r[ti].split()[0]), to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
+            continue
+        m = cpat.search(r[ki])
+        if m:
+            name = f"{'inv' if m.group(3) == '1' else 'fwd'}_level_k{m.group(2)}_c-3"
             best[name] = (float(r[ti].split()[0]), to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
             continue
         if "z_kernel<" in r[ki]:
