@@ -19,6 +19,7 @@ OUT = os.path.join(HERE, "libsnfft_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "snfft.h")
 
 MAIN_DEPS = [os.path.join(CSRC, f) for f in ("snfft.cu", "kernels.cuh", "plan.h", "base_gen.cuh")] + [HEADER]
+S6_DEPS = [os.path.join(CSRC, f) for f in ("s6_tu.cu", "s6_kernels.cuh", "s6_gen.cuh", "base_gen.cuh", "vec2.cuh")]
 PLAN_DEPS = [os.path.join(CSRC, f) for f in ("plan.cpp", "plan.h")]
 def col_deps(k):
     return [os.path.join(CSRC, f) for f in ("col_tu.cu", "col_kernels.cuh", f"col_gen_{k}.cuh")]
@@ -54,6 +55,8 @@ def units():
     u += [(os.path.join(OBJ, f"tz_{kind}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "tz_tu.cu"),
            [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"] + TZ_EXTRA, tz_deps(kind))
           for kind, f64, inv in TZ_COMBOS]
+    u += [(os.path.join(OBJ, f"s6_f32_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "s6_tu.cu"), [f"-DSNFFT_S6_INV={inv}"], S6_DEPS)
+          for inv in (0, 1)]
     u.insert(0, (os.path.join(OBJ, "snfft.o"), os.path.join(CSRC, "snfft.cu"), [], MAIN_DEPS))
     u.append((os.path.join(OBJ, "plan.o"), os.path.join(CSRC, "plan.cpp"), [], PLAN_DEPS))
     return u
@@ -63,7 +66,7 @@ def generate_col_headers(force: bool = False):
     """col_gen_<k>.cuh (20 MB of straight-line code) are not kept in git: csrc/gen_col.py writes them (2 s)."""
     for script, gen_names, head_names in (
             ("gen_col.py", ("gen_col.py", "gen_base.py"),
-             [f"col_gen_{k}.cuh" for k in (6, 7, 8)]),
+             [f"col_gen_{k}.cuh" for k in (6, 7, 8)] + ["s6_gen.cuh"]),
             ("gen_tz.py", ("gen_tz.py", "gen_col.py", "gen_base.py"),
              ["tz_gen_z7.cuh", "tz_gen_z8.cuh", "tz_gen_tab.cuh", "tz_gen_t9.cuh", "tz_gen_t10.cuh", "tz_gen_t11.cuh"])):
         gens = [os.path.join(CSRC, f) for f in gen_names]

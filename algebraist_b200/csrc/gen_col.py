@@ -483,6 +483,96 @@ def gen_level(k, inverse, only=None):
     return "\n".join(code), groups, task, total
 
 
+def gen_s6(inverse):
+    """Level-6 child-major tasks for the fused levels-2..6 kernel (s6_kernels.cuh): the level-5 side is a SHARED-MEMORY tile
+    [coefficient of S_5][coset][S6_LANES instances] that the threads of the same CTA fill (forward) or consume (inverse)
+    with the generated levels 2..5 code, so its stride is the compile-time S6_LANES; the level-6 side is the level array
+    X_6 in global memory with the run-time stride s.  Same operations as the level-6 column tasks of gen_level()."""
+    k = 6
+    tag = f"s6{'i' if inverse else 'f'}"
+    funcs, cases, items = [], [], []
+    for task, mu in enumerate(partitions(k - 1)):
+        dm = dim(mu)
+        em = ScaledEmitter()
+        cache = {}
+        if not inverse:
+            def load(r, i, em=em, cache=cache, dm=dm):
+                if (r, i) not in cache:
+                    cache[(r, i)] = em.tmp(f"sm[{r * dm * k + i} * S6_LANES]")
+                return cache[(r, i)]
+
+            for r in range(dm):
+                for i in range(k):
+                    load(r, i)
+            for lam in partitions(k):
+                if mu not in children(lam):
+                    continue
+                b = children(lam).index(mu)
+                bo, dl = boffs(lam)[b], dim(lam)
+
+                def store(t, v, em=em, lam=lam, dl=dl, bo=bo):
+                    em.lines.append(f"    x6[(size_t){coef_off(lam) + t * dl + bo} * s] = {value_expr(v)};")
+
+                forward_task(em, k, lam, b, list(range(dl)), load, store)
+            funcs.append("\n".join([
+                "template <typename T>",
+                f"__device__ __forceinline__ void {tag}_{task}(const T* __restrict__ sm, T* __restrict__ x6, unsigned s) {{"
+                f"   // all parents of {mu}"] + em.lines + ["}"]) + "\n")
+        else:
+            def load(lam, t, bo, em=em, cache=cache):
+                if (lam, t) not in cache:
+                    cache[(lam, t)] = em.tmp(f"x6[(size_t){coef_off(lam) + t * dim(lam) + bo} * s]")
+                return cache[(lam, t)]
+
+            for lam in partitions(k):
+                if mu in children(lam):
+                    bo = boffs(lam)[children(lam).index(mu)]
+                    for t in range(dim(lam)):
+                        load(lam, t, bo)
+            for i in range(k):
+                def store(r, v, em=em, i=i, dm=dm):
+                    em.lines.append(f"    sm[{r * dm * k + i} * S6_LANES] = {value_expr(v)};")
+
+                inverse_task(em, k, mu, i, list(range(dm)), load, store)
+            funcs.append("\n".join([
+                "template <typename T>",
+                f"__device__ __forceinline__ void {tag}_{task}(const T* __restrict__ x6, T* __restrict__ sm, unsigned s) {{"
+                f"   // {mu}, every coset"] + em.lines + ["}"]) + "\n")
+        cases.append(f"        case {task}: {tag}_{task}<T>(a, b, s); break;")
+        for c in range(dm):
+            items.append((em.n, task, c, coef_off(mu) + c))
+    code = funcs
+    code.append("\n".join([
+        "template <typename T, typename PA, typename PB>",
+        f"__device__ __forceinline__ void {tag}_run(int task, PA a, PB b, unsigned s) {{",
+        "    switch (task) {"] + cases + ["        default: break;", "    }", "}"]) + "\n")
+    items.sort(key=lambda it: -it[0])         # most expensive first: warp w takes the items w, w + NW, w + 2 NW, ..
+    return "\n".join(code), items
+
+
+def write_s6(here):
+    parts = ["// GENERATED by gen_col.py -- do not edit.  Level-6 tasks of the fused levels-2..6 kernel (s6_kernels.cuh): the",
+             "// level-5 side is a shared-memory tile with the compile-time instance stride S6_LANES.",
+             "#pragma once", "#include <stddef.h>", "#include \"vec2.cuh\"", "",
+             "#ifndef SNFFT_CODE_FENCE",
+             "#define SNFFT_CODE_FENCE() asm volatile(\"\" ::: \"memory\")",
+             "#endif", "",
+             "namespace snfft {", "namespace {", "",
+             "constexpr int S6_LANES = 32;      // instances of level 6 per CTA", ""]
+    for inverse in (False, True):
+        code, items = gen_s6(inverse)
+        parts.append(code)
+        d = "i" if inverse else "f"
+        parts.append(f"// (mu, c) columns of level 5 by decreasing cost: task = index of mu, c, coef_off(mu) + c")
+        parts.append(f"constexpr int S6_NITEMS = {len(items)};" if not inverse else "")
+        parts.append(f"static __device__ const unsigned char s6{d}_item_task[] = {{" + ", ".join(str(it[1]) for it in items) + "};")
+        parts.append(f"static __device__ const unsigned char s6{d}_item_c[] = {{" + ", ".join(str(it[2]) for it in items) + "};")
+        parts.append(f"static __device__ const unsigned char s6{d}_item_off[] = {{" + ", ".join(str(it[3]) for it in items) + "};")
+        parts.append("")
+    parts += ["}  // namespace", "}  // namespace snfft"]
+    write_if_changed(os.path.join(here, "s6_gen.cuh"), "\n".join(parts) + "\n")
+
+
 def header(k, codes, run_lines):
     parts = [f"// GENERATED by gen_col.py -- do not edit.  Register column code of the level step k = {k}",
              "// (see gen_col.py for the derivation and the reference citations).",
@@ -544,6 +634,7 @@ def main():
                              header(k, [code], ["    static_assert(!INV, \"forward only\");",
                                                 f"    col{k}f_run<T>(task, c, in, out, s);"]))
         stats[(k, False)] = tuple(tot)
+    write_s6(here)
     print("(level, inverse): (tasks, statements)", stats)
 
 

@@ -629,6 +629,32 @@ static int run_s5(const snfft_plan* p, const void* in, void* out, long long B, c
     return SNFFT_OK;
 }
 
+// Levels 2..6 in one kernel (s6_kernels.cuh / s6_tu.cu, fp32): the S_5 coefficients go from the generated levels-2..5
+// code to the level-6 column tasks through shared memory instead of a level array.  SNFFT_S6=0 keeps the two kernels.
+extern "C" {
+int snfft_s6_launch_f32_fwd(const void*, void*, long long, cudaStream_t);
+int snfft_s6_launch_f32_inv(const void*, void*, long long, cudaStream_t);
+}
+template <typename T>
+static bool s6_ok(const snfft_plan* p, bool inverse) {
+    static const bool on = [] {
+        const char* e = std::getenv("SNFFT_S6");
+        return !e || std::atoi(e) != 0;
+    }();
+    return on && sizeof(T) == 4 && p->n >= 6 && g_no_base.load() == 0 && (inverse ? p->lev[6].col_inv : p->lev[6].col_fwd);
+}
+// forward: in = X_1 (the gathered input), out = X_6; inverse: in = X_6, out = X_1.
+// Profile record: kind 4 / 5 (base kernel), level 6, kernel_class -8.
+template <typename T, bool INVERSE>
+static int run_s6(const snfft_plan* p, const void* in, void* out, long long B, cudaStream_t st) {
+    const long long ninst6 = B * (p->host.factorial[p->n] / 720);
+    ProfScope prof(p, st, INVERSE ? 5 : 4, 6, -8, 720);
+    const int rc = INVERSE ? snfft_s6_launch_f32_inv(in, out, ninst6, st) : snfft_s6_launch_f32_fwd(in, out, ninst6, st);
+    g_launches.fetch_add(1);
+    if (rc) return set_error(SNFFT_ECUDA, std::string("levels 2..6 kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return SNFFT_OK;
+}
+
 // Column kernels (col_kernels.cuh / col_tu.cu: one translation unit per level, dtype and direction).
 extern "C" {
 #define SNFFT_COL_DECL(k, dt) \
@@ -811,7 +837,11 @@ static int forward_levels(const snfft_plan* p, const void* f, long long B, void*
     if ((rc = run_gather<T, false>(p, f, cur, B, st))) return rc;
     int k_first = 2;
     const int base = g_no_base.load();          // 0: generated register kernels for levels 2..5, else table-driven level kernels
-    if (base == 0 && p->n > 5) {
+    if (s6_ok<T>(p, false) && (k_stop < 0 || k_stop > 6)) {
+        if ((rc = run_s6<T, false>(p, cur, nxt, B, st))) return rc;
+        std::swap(cur, nxt);
+        k_first = 7;
+    } else if (base == 0 && p->n > 5) {
         if ((rc = run_s5<T, false>(p, cur, nxt, B, st))) return rc;
         std::swap(cur, nxt);
         k_first = 6;
@@ -950,7 +980,8 @@ static int inverse_tail(const snfft_plan* p, int k_top, const void* cur, void** 
                         void* f, cudaStream_t st) {
     int rc;
     const int base = g_no_base.load();
-    const int k_last = (base == 0 && p->n > 5) ? 6 : 2;      // lowest level the per-level kernels handle
+    const bool s6 = s6_ok<T>(p, true) && k_top >= 6;
+    const int k_last = s6 ? 7 : ((base == 0 && p->n > 5) ? 6 : 2);      // lowest level the per-level kernels handle
     for (int k = k_top; k >= k_last; --k) {
         if (base == 0 && p->lev[k].tz_inv) rc = run_tz_level<T, true>(p, k, cur, bufs[which], zbuf, B, st);
         else if (base == 0 && p->lev[k].col_inv) rc = run_col_level<T, true>(p, k, cur, bufs[which], B, st);
@@ -959,7 +990,11 @@ static int inverse_tail(const snfft_plan* p, int k_top, const void* cur, void** 
         cur = bufs[which];
         which ^= 1;
     }
-    if (base == 0 && p->n > 5) {
+    if (s6) {
+        if ((rc = run_s6<T, true>(p, cur, bufs[which], B, st))) return rc;
+        cur = bufs[which];
+        which ^= 1;
+    } else if (base == 0 && p->n > 5) {
         if ((rc = run_s5<T, true>(p, cur, bufs[which], B, st))) return rc;
         cur = bufs[which];
         which ^= 1;

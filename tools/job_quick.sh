@@ -1,2 +1,3 @@
-timeout 170 ncu --set full --clock-control none --kernel-name-base demangled -k 'regex:col_kernel|s5_kernel' -f -o /tmp/prof_col python tools/prof_step.py --n 10 --batch 128 > gpurun_out/ncu_col_r01r.log 2>&1; echo "ncu rc=$?"
-python tools/ncu_summary.py /tmp/prof_col.ncu-rep gpurun_out/ncu_col_r01r.csv > /dev/null; echo "summary rc=$?"
+TAG=$1
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub-records > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+python tools/show_bench.py gpurun_out/bench_$TAG.json 2>/dev/null | head -24
