@@ -43,6 +43,15 @@ if os.environ.get("SNFFT_TZ_PK_TUNE"):          # tuning build: all three warp-t
     TZ_EXTRA = ["-DSNFFT_TZ_PK_TUNE=1"]
 else:
     TZ_EXTRA = []
+# threads per CTA of the F2 instantiation (fp32, two instances per thread) by level; default min(COL_THREADS, 384)
+COL_THREADS_V2 = {}
+
+
+def col_v2_flags(k, f64):
+    t = os.environ.get(f"SNFFT_COL{k}_V2_THREADS") or COL_THREADS_V2.get(k)
+    return [f"-DSNFFT_COL_THREADS_V2={int(t)}"] if t and not f64 else []
+
+
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
@@ -50,7 +59,7 @@ def units():
     """(object, source, extra flags, dependencies); the largest translation units first."""
     u = [(os.path.join(OBJ, f"col_{k}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}_t{COL_THREADS.get((k, f64), 128)}.o"), os.path.join(CSRC, "col_tu.cu"),
           [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}",
-           f"-DSNFFT_COL_THREADS={COL_THREADS.get((k, f64), 128)}"], col_deps(k))
+           f"-DSNFFT_COL_THREADS={COL_THREADS.get((k, f64), 128)}"] + col_v2_flags(k, f64), col_deps(k))
          for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
     u += [(os.path.join(OBJ, f"tz_{kind}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "tz_tu.cu"),
            [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"] + TZ_EXTRA, tz_deps(kind))

@@ -41,7 +41,10 @@ struct ColGroups {
 };
 
 // threads per CTA of the F2 instantiation (two instances per thread, the register footprint of the fp64 one)
-constexpr int COL_THREADS_V2 = COL_THREADS > 384 ? 384 : COL_THREADS;
+#ifndef SNFFT_COL_THREADS_V2
+#define SNFFT_COL_THREADS_V2 (SNFFT_COL_THREADS > 384 ? 384 : SNFFT_COL_THREADS)
+#endif
+constexpr int COL_THREADS_V2 = SNFFT_COL_THREADS_V2;
 
 template <int K, bool INV, int NT = COL_THREADS>
 inline ColGroups col_groups(long long ninst, int chunk) {

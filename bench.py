@@ -289,7 +289,7 @@ def device_record(lib, n, B, dtype, steps, warmup, world, dev, barrier, all_redu
                      "end_to_end_frac": value / world * alg_bytes_pair / 1e9 / peak,
                      "kernel_classes": "c-3 column kernels, c-4 Z kernel, c-5 T kernel (top / bottom split), c-7 top-level T kernel on the packed "
                                        "layout (pack / unpack fused), c-2 vector "
-                                       "gather / pack, c-1 generated levels 2..5, c>=0 sweep kernels"},
+                                       "gather / pack, c-1 generated levels 2..5, c-8 levels 2..6 in one kernel (fp32), c>=0 sweep kernels"},
         "kernels": kernels[:40],
     }
 

@@ -245,7 +245,8 @@ int snfft_dense_rep(snfft_plan_t* plan, int part, void* out, void* stream);
  *         -4 / -5 the Z / T kernel of a top / bottom level step (levels 9..11: tz_kernels.cuh),
  *         -6 small-batch gather / scatter and the B = 1 pack copy,
  *         -7 the T kernel of the TOP level reading / writing the packed coefficients itself (no pack / unpack launch:
- *            batches with full instance vectors, B % 4 == 0 fp32, B % 2 == 0 fp64)
+ *            batches with full instance vectors, B % 4 == 0 fp32, B % 2 == 0 fp64),
+ *         -8 levels 2..6 in one kernel (fp32, n >= 6; kind 4 / 5, level 6: s6_kernels.cuh)
  *   elems_per_instance: coefficients the launch produces per function
  *     (its share of k!; the launch reads as many; the Z kernel: MB/k of k!), so its algorithmic traffic
  *     is 2 * elems_per_instance * NINST_level * sizeof(dtype) bytes.

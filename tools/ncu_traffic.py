@@ -44,6 +44,11 @@ def main():
             name = f"{'inv' if m.group(3) == '1' else 'fwd'}_level_k{m.group(2)}_c{'-7' if m.group(4) == '1' else '-5'}"
             best[name] = (float(r[ti].split()[0]), to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
             continue
+        m = re.search(r"s6_kernel<float, (?:\(bool\))?([01])>", r[ki])
+        if m:
+            name = f"{'inv' if m.group(1) == '1' else 'fwd'}_base_k6_c-8"
+            best[name] = (float(r[ti].split()[0]), to_bytes(r[ri]) + to_bytes(r[wi]), r[ti])
+            continue
         m = cpat.search(r[ki])
         if m:
             name = f"{'inv' if m.group(3) == '1' else 'fwd'}_level_k{m.group(2)}_c-3"
