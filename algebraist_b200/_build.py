@@ -49,7 +49,11 @@ COL_THREADS_V2 = {}
 
 def col_v2_flags(k, f64):
     t = os.environ.get(f"SNFFT_COL{k}_V2_THREADS") or COL_THREADS_V2.get(k)
-    return [f"-DSNFFT_COL_THREADS_V2={int(t)}"] if t and not f64 else []
+    out = [f"-DSNFFT_COL_THREADS_V2={int(t)}"] if t and not f64 else []
+    r = os.environ.get(f"SNFFT_COL{k}_V2_REGS_THREADS")
+    if r and not f64:
+        out.append(f"-DSNFFT_COL_V2_REGS_THREADS={int(r)}")
+    return out
 
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]

@@ -69,8 +69,11 @@ inline ColGroups col_groups(long long ninst, int chunk) {
 
 // Register cap: ptxas hoists the (read-only) loads of a whole task as far as the register file allows, which without
 // a cap means 255 registers and spills; MINB CTAs per SM bound it (fp32: 102 registers, fp64: 170).
+#ifndef SNFFT_COL_V2_REGS_THREADS
+#define SNFFT_COL_V2_REGS_THREADS 384      // resident threads per SM the F2 / fp64 instantiations are compiled for (register cap 65536 / this)
+#endif
 template <typename T, int K, bool INV, int NT = COL_THREADS>
-__global__ void __launch_bounds__(NT, (sizeof(T) == 4 ? 640 : 384) / NT) col_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst,
+__global__ void __launch_bounds__(NT, (sizeof(T) == 4 ? 640 : SNFFT_COL_V2_REGS_THREADS) / NT) col_kernel(const T* __restrict__ in, T* __restrict__ out, long long ninst,
                                                           const ColGroups g) {
     const unsigned b = blockIdx.x;
     int gi = 0;

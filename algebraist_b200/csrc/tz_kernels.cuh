@@ -249,6 +249,7 @@ z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, int s_shift
 constexpr int T_HINTS = 512;
 struct TTasks {
     int ntasks, hint_shift;
+    int pk_ct_fastest;                   // packed kernels: consecutive warps walk the column tiles (1) or the instance tiles (0) first
     unsigned blk0[T_MAXTASKS + 1];       // first block of every task (d_alpha, d_mu per task: TzDev<K>, generated)
     unsigned short hint[T_HINTS + 1];    // hint[j] = the task that owns block j << hint_shift: the search starts there
 };
@@ -291,9 +292,19 @@ t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::co
         constexpr unsigned IW = 32 / TZ_PK_CW;
         const unsigned nip = (s + IW - 1) / IW, nct = (dmu + TZ_PK_CW - 1) / TZ_PK_CW;
         const unsigned lane = (unsigned)q & 31u, w = (unsigned)(q >> 5);
-        const unsigned rt = w / nip, ip = w - rt * nip;
-        r = rt / nct;
-        c = (rt - r * nct) * TZ_PK_CW + (lane % TZ_PK_CW);
+        unsigned ct, ip;
+        if (g.pk_ct_fastest) {
+            const unsigned ri = w / nct;
+            ct = w - ri * nct;
+            r = ri / nip;
+            ip = ri - r * nip;
+        } else {
+            const unsigned rt = w / nip;
+            ip = w - rt * nip;
+            r = rt / nct;
+            ct = rt - r * nct;
+        }
+        c = ct * TZ_PK_CW + (lane % TZ_PK_CW);
         inst = ip * IW + lane / TZ_PK_CW;
         if (c >= dmu || inst >= s) return;
     } else {

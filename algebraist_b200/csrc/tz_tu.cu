@@ -251,8 +251,14 @@ static int tz_t_launch(void* z, void* x, void* xk, long long ninst, int pk, cuda
         const int v = e ? std::atoi(e) : TZ_PK_CW_DEFAULT;
         return v == 8 || v == 32 ? v : 16;
     }();
+    static const int pk_order = [] {
+        // measured (S_10, B = 128): column tiles first 1.08 ms forward / 0.97 ms inverse, instance tiles first 1.12 / 0.97
+        const char* e = std::getenv("SNFFT_TZ_PK_ORDER");
+        return e ? std::atoi(e) : 1;
+    }();
     TTasks g;
     g.ntasks = L::ntasks;
+    g.pk_ct_fastest = pk_order;
     unsigned long long blk = 0;
     for (int t = 0; t < L::ntasks; ++t) {
         g.blk0[t] = (unsigned)blk;
