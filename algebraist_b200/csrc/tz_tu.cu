@@ -245,11 +245,16 @@ static int tz_t_launch(void* z, void* x, void* xk, long long ninst, int pk, cuda
     while (nv > 1 && (ninst % nv != 0 || align_bits % (sizeof(tz_t) * nv) != 0)) nv >>= 1;
     if (pk && (nv != nv_max || (uintptr_t)xk % sizeof(tz_t) != 0)) return (int)cudaErrorInvalidValue;
     ninst /= nv;
-    // columns per warp tile of the packed kernels (tz_kernels.cuh): SNFFT_TZ_PK_CW = 8 | 16 | 32 (tuning switch)
+    // columns per warp tile of the packed kernels (tz_kernels.cuh).  The tuning build (-DSNFFT_TZ_PK_TUNE) holds all three
+    // widths and SNFFT_TZ_PK_CW = 8 | 16 | 32 picks one; the product build has the measured default only.
     static const int pk_cw = [] {
+#ifdef SNFFT_TZ_PK_TUNE
         const char* e = std::getenv("SNFFT_TZ_PK_CW");
         const int v = e ? std::atoi(e) : TZ_PK_CW_DEFAULT;
-        return v == 8 || v == 32 ? v : 16;
+        return v == 8 || v == 16 || v == 32 ? v : TZ_PK_CW_DEFAULT;
+#else
+        return TZ_PK_CW_DEFAULT;
+#endif
     }();
     static const int pk_order = [] {
         // measured (S_10, B = 128): column tiles first 1.08 ms forward / 0.97 ms inverse, instance tiles first 1.12 / 0.97
@@ -296,10 +301,11 @@ static int tz_t_launch(void* z, void* x, void* xk, long long ninst, int pk, cuda
     if (pk) {
 #ifdef SNFFT_TZ_PK_TUNE
         if (pk_cw == 8) TZ_T_LAUNCH(VMAX, true, 8)
-        else if (pk_cw == 32) TZ_T_LAUNCH(VMAX, true, 32)
-        else
-#endif
+        else if (pk_cw == 16) TZ_T_LAUNCH(VMAX, true, 16)
+        else TZ_T_LAUNCH(VMAX, true, 32)
+#else
         TZ_T_LAUNCH(VMAX, true, TZ_PK_CW_DEFAULT)
+#endif
     } else if (nv == nv_max) {
         TZ_T_LAUNCH(VMAX, false, 16)
     } else if (nv == 2) {
