@@ -69,13 +69,13 @@ def workload_name(a):
 
 def measured_traffic(kernel, batch, dtype, n=10):
     """DRAM bytes per launch of `kernel` from the committed ncu capture of THIS round's kernels
-    (profiles/r02*traffic*.json, written by tools/ncu_traffic.py from `ncu --set full`; each record names the
+    (profiles/r02* / r03* ... traffic*.json, written by tools/ncu_traffic.py from `ncu --set full`; each record names the
     capture and the commit it was taken on), or None when no capture of the current kernels matches."""
     best = None
     pdir = os.path.join(ROOT, "profiles")
     try:
         for fn in sorted(os.listdir(pdir)):
-            if fn.startswith("r02") and "traffic" in fn and fn.endswith(".json"):
+            if fn[:2] == "r0" and fn[2:3] in "23456789" and "traffic" in fn and fn.endswith(".json"):
                 with open(os.path.join(pdir, fn)) as fh:
                     for rec in json.load(fh):
                         if (rec.get("kernel") == kernel and rec.get("batch") == batch and rec.get("dtype") == dtype
