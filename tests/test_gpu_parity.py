@@ -81,6 +81,26 @@ def test_vs_oracle_large_n(A, n, B, dt):
     assert rel_err(got.cpu().numpy(), ref_inv) < TOL[dt]
 
 
+@pytest.mark.parametrize("n,B,rows", [(10, 128, (0, 77, 127)), (9, 1024, (0, 511, 1023))])
+def test_full_size_batches_rows_vs_oracle(A, n, B, rows):
+    """BASELINE configs 3 and 4 at their FULL batch sizes (S_9 x 1024, S_10 x 128, fp32): the rows `rows` of the
+    transform of the whole batch against the oracle's transform of those functions (every partition, 1e-5), and
+    the same rows of the inverse of the whole coefficient set against the inputs.  (The first / a middle / the last
+    row sit in different instance vectors, tiles and CTAs of every kernel.)"""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(31 * n + B)
+    x = torch.randn(B, math.factorial(n), device="cuda", generator=g)
+    ft = A.sn_fft(x, n)
+    sel = list(rows)
+    ref = O.sn_fft_packed_c(x[sel].double().cpu().numpy(), n)
+    _check_dict({lam: v[sel] for lam, v in ft.items()}, ref, 1e-5)
+    back = A.sn_ifft(ft, n)
+    assert rel_err(back[sel].cpu().numpy(), x[sel].cpu().numpy()) < 1e-5
+    # the oracle's inverse of the device coefficients of those rows agrees with the device inverse
+    coef = {lam: v[sel].double().cpu().numpy().reshape(len(sel), O.dim(lam), O.dim(lam)) for lam, v in ft.items()}
+    assert rel_err(back[sel].cpu().numpy(), O.sn_ifft_packed_c(coef, n)) < 1e-5
+
+
 @pytest.mark.parametrize("n,B,dt", [(8, 512, "f32"), (9, 128, "f32"), (10, 16, "f32"), (10, 8, "f64")])
 def test_properties_at_size(A, n, B, dt):
     """Round trip, Plancherel and linearity on a full-width batch (reference tests/test_fourier.py:55-84)."""
