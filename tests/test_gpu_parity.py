@@ -298,6 +298,20 @@ def test_vs_oracle_n11(A):
     ref = O.sn_fft_packed_c(f, n)
     ft = A.sn_fft(torch.from_numpy(f[0]).float().cuda(), n)
     _check_dict(ft, ref, TOL["f32"])
+    # the same function as row 2 of a batch of 4: full instance vectors, so level 11 runs the T kernel on the packed
+    # layout (MB = 8 bottom operators, three top sweeps) and the inverse reads the packed coefficients; rows 0, 1, 3
+    # are other functions
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1111)
+    x = torch.randn(4, math.factorial(n), device="cuda", generator=g)
+    x[2] = torch.from_numpy(f[0]).float().cuda()
+    ft4 = A.sn_fft(x, n)
+    _check_dict({lam: v[2:3] for lam, v in ft4.items()}, ref, TOL["f32"])
+    for lam, v in ft.items():                # scalar threads (B = 1) and vector threads run the same arithmetic in the
+        w = ft4[lam][2]                      # same order: identical values
+        assert torch.equal(w.reshape(v.shape), v), lam
+    back = A.sn_ifft(ft4, n)
+    assert rel_err(back.cpu().numpy(), x.cpu().numpy()) < TOL["f32"]
 
 
 @pytest.mark.parametrize("n,dt", [(5, "f64"), (7, "f32"), (8, "f64")])
