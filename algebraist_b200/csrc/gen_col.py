@@ -39,7 +39,7 @@ INV_COSETS_PER_TASK = {7: int(os.environ.get("SNFFT_GEN_INV_COSETS_7", "4")), 8:
 # ... and at most this many running sums per inverse task (cosets x rows of mu): the two d = 35 shapes of level 7 with two
 # cosets (70 sums) spilled 0.5-1.3 KB per thread in the six tasks that do most of level 8's work (profiles r02u: 2.2 GB
 # written for 1.86 GB of output); they run one coset per task
-INV_SUMS_CAP = {7: int(os.environ.get("SNFFT_GEN_INV_SUMS_7", "64")), 8: int(os.environ.get("SNFFT_GEN_INV_SUMS_8", "48"))}
+INV_SUMS_CAP = {7: int(os.environ.get("SNFFT_GEN_INV_SUMS_7", "48")), 8: int(os.environ.get("SNFFT_GEN_INV_SUMS_8", "48"))}
 
 
 def inv_cosets(k, d):
@@ -50,8 +50,10 @@ def inv_cosets(k, d):
 SPLIT_FWD = {}            # forward-only levels generated in parts (level 9, until the top / bottom kernels of gen_tz.py took it over)
 # forward tasks: rows of output a task owns at most (level 8: adjacent child blocks are merged up to this many rows,
 # so that small blocks share their loads; level 7: several parents of one child shape per task, as many as fit this
-# many running sums)
-FWD_ROWS_CAP = {7: int(os.environ.get("SNFFT_GEN_FWD_ROWS_7", "70")), 8: int(os.environ.get("SNFFT_GEN_FWD_ROWS_8", "35"))}
+# many running sums).  Level 7 / Z kernels with F2 threads, measured (S_10, B = 128): 35 / 42 / 48 / 56 / 70 sums ->
+# level 7 forward 0.69 / 0.67 / 0.67 / 0.68 / 0.70 ms, Z forward of level 9 0.56 / 0.56 / 0.55 / 0.58 / 0.61 ms; inverse
+# sums cap 48 against 64 at level 7: 0.65 / 0.66 ms; 35 against 48 at level 8: 1.11 / 1.04 ms
+FWD_ROWS_CAP = {7: int(os.environ.get("SNFFT_GEN_FWD_ROWS_7", "48")), 8: int(os.environ.get("SNFFT_GEN_FWD_ROWS_8", "35"))}
 
 
 def partner_checked(part, j, t):
