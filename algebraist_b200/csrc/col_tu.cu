@@ -64,7 +64,9 @@ extern "C" int COL_NAME(const void* in, void* out, long long ninst, cudaStream_t
             std::snprintf(name, sizeof name, "SNFFT_COL_CHUNK2_%d", SNFFT_COL_K);
             const char* e = std::getenv(name);
             if (e) return std::atoi(e);
-            return SNFFT_COL_K == 8 ? 8 : (SNFFT_COL_K == 7 && SNFFT_COL_INV ? 37 : 74);
+            // measured (profiles r03n): level 7 forward 18..296 tiles within 1 %, inverse 0.65 / 0.65 / 0.66 / 0.67 / 0.69 ms at
+            // 18 / 37 / 74 / 148 / 296; level 8: 4..32 within 2 %
+            return SNFFT_COL_K == 8 ? 8 : (SNFFT_COL_K == 7 && SNFFT_COL_INV ? 37 : 148);
         }();
         const long long n2 = ninst / 2;
         const ColGroups g2 = col_groups<SNFFT_COL_K, SNFFT_COL_INV != 0, COL_THREADS_V2>(n2, chunk2);

@@ -167,7 +167,9 @@ extern "C" int TZ_ZNAME(int k, const void* src, void* dst, long long ninst, cuda
     }();
     static const int chunk2 = [] {
         const char* e = std::getenv("SNFFT_TZ_CHUNK2");
-        return e ? std::atoi(e) : (SNFFT_TZ_INV ? 37 : 74);
+        // measured (profiles r03n, Z of level 9): forward 0.56 / 0.56 / 0.55 / 0.54 / 0.56 ms at 18 / 37 / 74 / 148 / 296
+        // tiles, inverse 0.52 / 0.52 / 0.52 / 0.54 / 0.55 ms
+        return e ? std::atoi(e) : (SNFFT_TZ_INV ? 37 : 148);
     }();
     v2 = v2_on && ninst % 2 == 0 && ((uintptr_t)src | (uintptr_t)dst) % sizeof(F2) == 0;
     if (v2) {
