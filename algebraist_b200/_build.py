@@ -39,6 +39,10 @@ COL_COMBOS = [(k, f64, inv) for k in (6, 7, 8) for f64 in (0, 1) for inv in (0, 
 # different tasks per SM): forward k = 9 3.36 -> 2.30 ms, fp64 5.6 -> 3.7 ms; level 7 is faster with 128.
 COL_THREADS = {(8, 0): 640, (8, 1): 384}
 
+if os.environ.get("SNFFT_T_THREADS"):           # tuning build: CTA size of the T kernels
+    TZ_T = [f"-DSNFFT_T_THREADS={int(os.environ['SNFFT_T_THREADS'])}"]
+else:
+    TZ_T = []
 if os.environ.get("SNFFT_TZ_PK_TUNE"):          # tuning build: all three warp-tile widths of the packed T kernels (SNFFT_TZ_PK_CW picks)
     TZ_EXTRA = ["-DSNFFT_TZ_PK_TUNE=1"]
 else:
@@ -66,7 +70,7 @@ def units():
            f"-DSNFFT_COL_THREADS={COL_THREADS.get((k, f64), 128)}"] + col_v2_flags(k, f64), col_deps(k))
          for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
     u += [(os.path.join(OBJ, f"tz_{kind}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "tz_tu.cu"),
-           [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"] + TZ_EXTRA, tz_deps(kind))
+           [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"] + TZ_EXTRA + TZ_T, tz_deps(kind))
           for kind, f64, inv in TZ_COMBOS]
     u += [(os.path.join(OBJ, f"s6_f32_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "s6_tu.cu"), [f"-DSNFFT_S6_INV={inv}"], S6_DEPS)
           for inv in (0, 1)]

@@ -171,7 +171,13 @@ namespace snfft {
 namespace {
 
 constexpr int Z_THREADS = 128;
-constexpr int T_THREADS = 256;
+// threads per CTA of the T kernels; measured (S_10, B = 128, profiles r03o): 256 / 128 / 64 -> level 9 0.71 / 0.66 / 0.66 ms,
+// level 10 on the packed layout 1.08 / 1.05 / 1.05 ms forward, 0.97 / 0.94 / 0.94 ms inverse (smaller CTAs retire and
+// refill more evenly: every thread runs one straight-line function and exits)
+#ifndef SNFFT_T_THREADS
+#define SNFFT_T_THREADS 128
+#endif
+constexpr int T_THREADS = SNFFT_T_THREADS;
 constexpr int Z_MAXGROUPS = 15;          // partitions of MB - 1 = 6 (11) or 7 (15)
 constexpr int T_MAXTASKS = 512;
 
@@ -260,8 +266,8 @@ struct TTasks {
 // measured: 0.78 -> 0.97 ms at k = 9 -- 400 k empty CTAs are not free -- so the task is found by binary search.)
 // PK = true (top level, T = TzVec<S, NV>): the level-k side is the public packed layout (TzAcc).  A warp is then a tile
 // of TZ_PK_CW (template parameter) columns x 32 / TZ_PK_CW instance vectors of one row r: the instance-fastest side (Z, X_{k-1}) moves runs of
-// NV * 32 / TZ_PK_CW instances per column, the packed side runs of TZ_PK_CW columns per batch row; the tiles of one
-// (r, column tile) over the whole batch are adjacent (same CTA for B <= 8 * NV * 32 / TZ_PK_CW).
+// NV * 32 / TZ_PK_CW instances per column, the packed side runs of TZ_PK_CW columns per batch row; consecutive warps
+// walk the column tiles of one (r, instance tile) first (TTasks::pk_ct_fastest), i.e. along the rows of F_lambda.
 // cw = 0: not packed
 __host__ __device__ __forceinline__ unsigned long long t_task_lanes(unsigned dal, unsigned dmu, unsigned s, unsigned cw) {
     if (cw == 0) return (unsigned long long)dal * dmu * s;
@@ -270,7 +276,7 @@ __host__ __device__ __forceinline__ unsigned long long t_task_lanes(unsigned dal
 }
 
 template <typename T, int K, bool INV, bool PK, int TZ_PK_CW = 16>
-__global__ void __launch_bounds__(T_THREADS, 2)
+__global__ void __launch_bounds__(T_THREADS, 512 / T_THREADS)
 t_kernel(typename std::conditional<INV, T*, const T*>::type zb, typename std::conditional<INV, T*, const T*>::type xb,
          typename std::conditional<INV, const T*, T*>::type lb, unsigned s, int s_shift, const TTasks g) {
     const unsigned b = blockIdx.x;
