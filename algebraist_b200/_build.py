@@ -43,6 +43,8 @@ if os.environ.get("SNFFT_T_THREADS"):           # tuning build: CTA size of the 
     TZ_T = [f"-DSNFFT_T_THREADS={int(os.environ['SNFFT_T_THREADS'])}"]
 else:
     TZ_T = []
+if os.environ.get("SNFFT_Z_THREADS"):           # tuning build: CTA size of the Z kernels
+    TZ_T += [f"-DSNFFT_Z_THREADS={int(os.environ['SNFFT_Z_THREADS'])}"]
 if os.environ.get("SNFFT_TZ_PK_TUNE"):          # tuning build: all three warp-tile widths of the packed T kernels (SNFFT_TZ_PK_CW picks)
     TZ_EXTRA = ["-DSNFFT_TZ_PK_TUNE=1"]
 else:

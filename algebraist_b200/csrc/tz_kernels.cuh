@@ -170,7 +170,10 @@ struct TzAcc<TzVec<S, NV>, true, CONST> {
 namespace snfft {
 namespace {
 
-constexpr int Z_THREADS = 128;
+#ifndef SNFFT_Z_THREADS
+#define SNFFT_Z_THREADS 128
+#endif
+constexpr int Z_THREADS = SNFFT_Z_THREADS;
 // threads per CTA of the T kernels; measured (S_10, B = 128, profiles r03o): 256 / 128 / 64 -> level 9 0.71 / 0.66 / 0.66 ms,
 // level 10 on the packed layout 1.08 / 1.05 / 1.05 ms forward, 0.97 / 0.94 / 0.94 ms inverse (smaller CTAs retire and
 // refill more evenly: every thread runs one straight-line function and exits)
