@@ -53,13 +53,25 @@ else:
 COL_THREADS_V2 = {}
 
 
-def col_v2_flags(k, f64):
+# resident threads per SM the F2 instantiations are compiled for (register cap 65536 / this; default 384 = 168 registers).
+# With 48 running sums per forward task the level-7 code fits 128 registers: four CTAs of 128 threads per SM
+# (level 7 forward 0.67 -> 0.64 ms; the inverse tasks spill under that cap: 0.66 -> 0.67 ms)
+COL_V2_REGS_THREADS = {(7, 0): 512}
+Z_V2_REGS_THREADS = {}          # the Z kernels (run-time strides, segment lookup) lose under the same cap: 0.55 -> 0.57 ms
+
+
+def col_v2_flags(k, f64, inv=0):
     t = os.environ.get(f"SNFFT_COL{k}_V2_THREADS") or COL_THREADS_V2.get(k)
     out = [f"-DSNFFT_COL_THREADS_V2={int(t)}"] if t and not f64 else []
-    r = os.environ.get(f"SNFFT_COL{k}_V2_REGS_THREADS")
+    r = os.environ.get(f"SNFFT_COL{k}_V2_REGS_THREADS") or COL_V2_REGS_THREADS.get((k, inv))
     if r and not f64:
         out.append(f"-DSNFFT_COL_V2_REGS_THREADS={int(r)}")
     return out
+
+
+def z_v2_flags(kind, f64, inv):
+    r = os.environ.get("SNFFT_Z_V2_REGS_THREADS") or Z_V2_REGS_THREADS.get((kind, inv))
+    return [f"-DSNFFT_Z_V2_REGS_THREADS={int(r)}"] if r and not f64 and kind in (7, 8) else []
 
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
@@ -69,10 +81,10 @@ def units():
     """(object, source, extra flags, dependencies); the largest translation units first."""
     u = [(os.path.join(OBJ, f"col_{k}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}_t{COL_THREADS.get((k, f64), 128)}.o"), os.path.join(CSRC, "col_tu.cu"),
           [f"-DSNFFT_COL_K={k}", f"-DSNFFT_COL_F64={f64}", f"-DSNFFT_COL_INV={inv}",
-           f"-DSNFFT_COL_THREADS={COL_THREADS.get((k, f64), 128)}"] + col_v2_flags(k, f64), col_deps(k))
+           f"-DSNFFT_COL_THREADS={COL_THREADS.get((k, f64), 128)}"] + col_v2_flags(k, f64, inv), col_deps(k))
          for k, f64, inv in sorted(COL_COMBOS, reverse=True)]
     u += [(os.path.join(OBJ, f"tz_{kind}_{'f64' if f64 else 'f32'}_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "tz_tu.cu"),
-           [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"] + TZ_EXTRA + TZ_T, tz_deps(kind))
+           [f"-DSNFFT_TZ_KIND={kind}", f"-DSNFFT_TZ_F64={f64}", f"-DSNFFT_TZ_INV={inv}"] + TZ_EXTRA + TZ_T + z_v2_flags(kind, f64, inv), tz_deps(kind))
           for kind, f64, inv in TZ_COMBOS]
     u += [(os.path.join(OBJ, f"s6_f32_{'inv' if inv else 'fwd'}.o"), os.path.join(CSRC, "s6_tu.cu"), [f"-DSNFFT_S6_INV={inv}"], S6_DEPS)
           for inv in (0, 1)]

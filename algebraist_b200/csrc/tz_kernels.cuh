@@ -205,7 +205,10 @@ struct ZGroups {
 
 #if SNFFT_TZ_KIND == 7 || SNFFT_TZ_KIND == 8
 template <typename T, bool INV>
-__global__ void __launch_bounds__(Z_THREADS, (sizeof(T) == 4 ? 640 : 384) / Z_THREADS)
+#ifndef SNFFT_Z_V2_REGS_THREADS
+#define SNFFT_Z_V2_REGS_THREADS 384        // resident threads per SM the F2 / fp64 instantiations are compiled for (register cap 65536 / this)
+#endif
+__global__ void __launch_bounds__(Z_THREADS, (sizeof(T) == 4 ? 640 : SNFFT_Z_V2_REGS_THREADS) / Z_THREADS)
 z_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned s, int s_shift, const ZGroups g,
          const ZSeg* __restrict__ segs, const unsigned* __restrict__ unit2seg) {
     const unsigned b = blockIdx.x;
