@@ -781,18 +781,40 @@ __global__ void __launch_bounds__(256) gather_vec_kernel(const T* __restrict__ i
         const long long r = r0 + rq + 32 * it;
         p1[it] = r < ia.nfact ? (p1tab ? (long long)p1tab[r] : chain_index(ia.n, r, ia.fact)) : -1;
     }
+    // the loads of the NEXT batch tile are issued before the barrier of the current one (one DRAM latency per tile off the
+    // critical path of a CTA)
+    PV nxt[VT];
+    auto load_f = [&](long long b0, PV (&dst)[VT]) {             // dst[i] = f[b0 + VT*bq + i][r0 + VT*cb ..]
+#pragma unroll
+        for (int i = 0; i < VT; ++i) {
+            const long long b = b0 + VT * bq + i;
+            if (f_ok && b < ia.batch) dst[i] = *reinterpret_cast<const PV*>(in + b * ia.nfact + r0 + VT * cb);
+            else {
+#pragma unroll
+                for (int v = 0; v < VT; ++v) dst[i].v[v] = T(0);
+            }
+        }
+    };
+    auto load_x = [&](long long b0, PV (&dst)[VT]) {             // dst[it] = x1[p1(rank rq + 32*it)][b0 + VT*ch ..]
+#pragma unroll
+        for (int it = 0; it < VT; ++it) {
+            const long long b = b0 + VT * ch;
+            if (p1[it] >= 0 && b < ia.batch) dst[it] = *reinterpret_cast<const PV*>(in + p1[it] * ia.batch + b);
+            else {
+#pragma unroll
+                for (int q = 0; q < VT; ++q) dst[it].v[q] = T(0);
+            }
+        }
+    };
+    if (ia.batch > 0) {
+        if (!SCATTER) load_f(0, nxt);
+        else load_x(0, nxt);
+    }
     for (long long b0 = 0; b0 < ia.batch; b0 += TB) {
         if (!SCATTER) {
-            PV blk[VT];                                          // blk[i] = f[b0 + VT*bq + i][r0 + VT*cb ..]
+            PV blk[VT];
 #pragma unroll
-            for (int i = 0; i < VT; ++i) {
-                const long long b = b0 + VT * bq + i;
-                if (f_ok && b < ia.batch) blk[i] = *reinterpret_cast<const PV*>(in + b * ia.nfact + r0 + VT * cb);
-                else {
-#pragma unroll
-                    for (int v = 0; v < VT; ++v) blk[i].v[v] = T(0);
-                }
-            }
+            for (int i = 0; i < VT; ++i) blk[i] = nxt[i];
 #pragma unroll
             for (int j = 0; j < VT; ++j) {                       // rank VT*cb + j, batch chunk bq
                 PV col;
@@ -800,6 +822,7 @@ __global__ void __launch_bounds__(256) gather_vec_kernel(const T* __restrict__ i
                 for (int i = 0; i < VT; ++i) col.v[i] = blk[i].v[j];
                 *reinterpret_cast<PV*>(tile + (VT * cb + j) * TB + ((bq ^ (cb & 7)) * VT)) = col;
             }
+            if (b0 + TB < ia.batch) load_f(b0 + TB, nxt);
             __syncthreads();
 #pragma unroll
             for (int it = 0; it < VT; ++it) {
@@ -814,15 +837,9 @@ __global__ void __launch_bounds__(256) gather_vec_kernel(const T* __restrict__ i
 #pragma unroll
             for (int it = 0; it < VT; ++it) {
                 const int rr = rq + 32 * it;
-                const long long b = b0 + VT * ch;
-                PV v;
-                if (p1[it] >= 0 && b < ia.batch) v = *reinterpret_cast<const PV*>(in + p1[it] * ia.batch + b);
-                else {
-#pragma unroll
-                    for (int q = 0; q < VT; ++q) v.v[q] = T(0);
-                }
-                *reinterpret_cast<PV*>(tile + rr * TB + ((ch ^ ((rr / VT) & 7)) * VT)) = v;
+                *reinterpret_cast<PV*>(tile + rr * TB + ((ch ^ ((rr / VT) & 7)) * VT)) = nxt[it];
             }
+            if (b0 + TB < ia.batch) load_x(b0 + TB, nxt);
             __syncthreads();
             PV col[VT];
 #pragma unroll

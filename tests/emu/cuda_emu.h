@@ -63,7 +63,14 @@ struct Sched {
     std::vector<char> done;
     const std::function<void()>* body = nullptr;
     int cur = 0;
-    static constexpr size_t kStack = 64 * 1024;
+    // per emulated thread.  The generated straight-line task functions hold every temporary in their frame at -O1 (and
+    // AddressSanitizer puts redzones around each: an F2 level-8 task overflowed 64 KB stacks in the sanitizer build, which
+    // corrupted the heap next to the stack array before ASan reported it)
+#if defined(__SANITIZE_ADDRESS__)
+    static constexpr size_t kStack = 1024 * 1024;
+#else
+    static constexpr size_t kStack = 256 * 1024;
+#endif
 };
 inline Sched g;
 

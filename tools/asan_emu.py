@@ -66,7 +66,10 @@ def cases():
         print(done[-1], flush=True)
 
     for n, B, dt in ((6, 5, np.float32), (7, 4, np.float32), (7, 3, np.float64), (8, 2, np.float64), (8, 4, np.float32),
-                     (9, 1, np.float64), (9, 4, np.float32), (9, 3, np.float32)):
+                     (9, 1, np.float64), (9, 4, np.float32), (9, 3, np.float32),
+                     # (6, 4): levels 2..6 kernel + pack; (9, 2) fp64 / (9, 4) fp32 above: T kernel on the packed layout,
+                     # F2 column / Z kernels (fp32)
+                     (6, 4, np.float32), (9, 2, np.float64)):
         run(n, B, dt, "auto")
     for mode in (0,):
         emu.snfft_debug_tb_mode(mode)
