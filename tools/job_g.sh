@@ -1,3 +1,7 @@
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub-records > gpurun_out/bench_r04w.json 2> gpurun_out/bench_r04w.err; echo "bench rc=$?"
-python tools/show_bench.py gpurun_out/bench_r04w.json 2>/dev/null | grep -E 'transforms|gather|scatter'
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or ragged or host" 2>&1 | tail -2
+# last check of the round: bench line + full GPU suite + smoke on the final code
+TAG=$1
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench rc=$?"
+python tools/show_bench.py gpurun_out/bench_${TAG}.json 2>/dev/null | head -8
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest_gpu_$TAG.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
