@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "base_gen.cuh"
+#include "vec2.cuh"
 
 namespace snfft {
 
@@ -1178,7 +1179,8 @@ __global__ void __launch_bounds__(256) translate_kernel(const T* __restrict__ f,
 // Per-partition products of two packed coefficient arrays: C_lambda[b] = A_lambda[b] . B_lambda[b]
 // (d x d, row major), the Fourier side of the convolution theorem (reference tests/test_fourier.py:87-109).
 // One launch for all partitions; a CTA owns a 64 x 64 tile of one batch row of one partition, 256 threads x (4 x 4) outputs,
-// K in steps of 16 through shared memory (A stored transposed so both operand reads are conflict free).
+// K in steps of 16 through shared memory (A stored transposed so both operand reads are conflict free); fp32 partitions
+// with d >= MMParts::big_min: 128 x 128 tiles, 8 x 8 outputs per thread (block_matmul_big).
 // Plain FFMA / DFMA: the parity contract is fp32 1e-5 / fp64 1e-12, which rules out the TF32 tensor path.
 // ---------------------------------------------------------------------------
 constexpr int MM_TILE = 64, MM_K = 16, MM_THREADS = 256;
@@ -1188,29 +1190,112 @@ constexpr int MM_TILE = 64, MM_K = 16, MM_THREADS = 256;
 constexpr int MM_MAXPARTS = 80;          // 77 partitions at n = 12
 struct MMParts {
     int nparts;
+    int big_min;                         // fp32: partitions with d >= big_min run the 128 x 128 tile path
     int d[MM_MAXPARTS];
     long long blk0[MM_MAXPARTS + 1];
     long long off[MM_MAXPARTS];
 };
+constexpr int MM_BIG = 128, MM_BIG_K = 8;
+__host__ __device__ inline int mm_tile_of(int d, int big_min, bool f32) { return f32 && d >= big_min ? MM_BIG : MM_TILE; }
+
+// fp32, large partitions: a CTA owns a 128 x 128 tile, a thread 8 x 8 outputs as four 4 x 4 blocks (rows ty*4.., 64+ty*4..,
+// columns tx*4.., 64+tx*4..: every operand read is one conflict-free 16-byte shared load, 64 FMA per 4 loads), K in steps
+// of 8, the next K step's global loads issued before the arithmetic of the current one.
+__device__ __forceinline__ void block_matmul_big(const float* __restrict__ a, const float* __restrict__ bm, float* __restrict__ c,
+                                                 int d, int m0, int n0, float (&As)[MM_BIG_K][MM_BIG + 4],
+                                                 float (&Bs)[MM_BIG_K][MM_BIG + 4]) {
+    const int tid = threadIdx.x;
+    const int ty = tid / 16, tx = tid % 16;
+    // loaders: A tile 128 rows x 8 k -> thread (row = tid / 2, k = 4 (tid % 2) ..+3); B tile 8 k x 128 columns -> thread
+    // (k = tid / 32, column = 4 (tid % 32) ..+3).  Scalar loads: d is not a multiple of 4 in general.
+    const int ar = tid / 2, ak = (tid % 2) * 4;
+    const int bk = tid / 32, bc = (tid % 32) * 4;
+    float pa[4], pb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            pa[q] = (m0 + ar < d && k0 + ak + q < d) ? a[(size_t)(m0 + ar) * d + k0 + ak + q] : 0.f;
+            pb[q] = (k0 + bk < d && n0 + bc + q < d) ? bm[(size_t)(k0 + bk) * d + n0 + bc + q] : 0.f;
+        }
+    };
+    // accumulators as pairs of ROWS (2p, 2p + 1): one FFMA2 (fma.rn.f32x2) per pair and column, the A operand pairs come
+    // straight out of the 16-byte shared loads, the B operand is duplicated into both halves (8 MOV per 32 FFMA2)
+    F2 acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = F2(0.0);
+    fetch(0);
+    for (int k0 = 0; k0 < d; k0 += MM_BIG_K) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            As[ak + q][ar] = pa[q];
+            Bs[bk][bc + q] = pb[q];
+        }
+        __syncthreads();
+        if (k0 + MM_BIG_K < d) fetch(k0 + MM_BIG_K);
+#pragma unroll
+        for (int kk = 0; kk < MM_BIG_K; ++kk) {
+            float av[8], bv[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                av[i] = As[kk][ty * 4 + i];
+                av[4 + i] = As[kk][64 + ty * 4 + i];
+                bv[i] = Bs[kk][tx * 4 + i];
+                bv[4 + i] = Bs[kk][64 + tx * 4 + i];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                F2 b2;
+                b2.x = bv[j];
+                b2.y = bv[j];
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                    F2 a2;
+                    a2.x = av[2 * pr];
+                    a2.y = av[2 * pr + 1];
+                    acc[pr][j] = sn_fma(a2, b2, acc[pr][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4), cc = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+            if (r < d && cc < d) c[(size_t)r * d + cc] = (i & 1) ? acc[i / 2][j].y : acc[i / 2][j].x;
+        }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(MM_THREADS) block_matmul_kernel(const T* __restrict__ A, const T* __restrict__ B,
                                                                   T* __restrict__ C, const MMParts mp) {
-    __shared__ T As[MM_K][MM_TILE + 4];
-    __shared__ T Bs[MM_K][MM_TILE + 4];
     const int tid = threadIdx.x;
     int part = 0;
     while (part + 1 < mp.nparts && (long long)blockIdx.x >= mp.blk0[part + 1]) ++part;
-    const int d = mp.d[part], tiles = (d + MM_TILE - 1) / MM_TILE;
+    const int d = mp.d[part];
+    const int tile = mm_tile_of(d, mp.big_min, sizeof(T) == 4), tiles = (d + tile - 1) / tile;
     A += mp.off[part];
     B += mp.off[part];
     C += mp.off[part];
     const long long blk = (long long)blockIdx.x - mp.blk0[part];
     const long long b = blk / ((long long)tiles * tiles);
     const int rem = (int)(blk - b * (long long)tiles * tiles);
-    const int m0 = (rem / tiles) * MM_TILE, n0 = (rem % tiles) * MM_TILE;
+    const int m0 = (rem / tiles) * tile, n0 = (rem % tiles) * tile;
     const T* __restrict__ a = A + (size_t)b * d * d;
     const T* __restrict__ bm = B + (size_t)b * d * d;
+    if constexpr (sizeof(T) == 4) {
+        __shared__ float Ab[MM_BIG_K][MM_BIG + 4];
+        __shared__ float Bb[MM_BIG_K][MM_BIG + 4];
+        if (tile == MM_BIG) {             // uniform per CTA
+            block_matmul_big((const float*)a, (const float*)bm, (float*)(C + (size_t)b * d * d), d, m0, n0, Ab, Bb);
+            return;
+        }
+    }
+    __shared__ T As[MM_K][MM_TILE + 4];
+    __shared__ T Bs[MM_K][MM_TILE + 4];
     const int ty = tid / 16, tx = tid % 16;
     T acc[4][4];
 #pragma unroll

@@ -1548,10 +1548,16 @@ int snfft_block_matmul(const snfft_plan_t* p, const void* A, const void* Bm, voi
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return L.shapes[x].dim > L.shapes[y].dim; });
     MMParts mp;
     mp.nparts = (int)order.size();
+    // smallest d that runs the 128 x 128 tile path (fp32); SNFFT_MM_BIG_MIN overrides (1 = every partition: tests)
+    mp.big_min = [] {
+        const char* e = std::getenv("SNFFT_MM_BIG_MIN");
+        return e ? std::atoi(e) : 160;
+    }();
     long long nblk = 0;
     for (size_t i = 0; i < order.size(); ++i) {
         const int d = L.shapes[order[i]].dim;
-        const long long tiles = (d + MM_TILE - 1) / MM_TILE;
+        const int tile = mm_tile_of(d, mp.big_min, p->dtype == SNFFT_F32);
+        const long long tiles = (d + tile - 1) / tile;
         mp.d[i] = d;
         mp.blk0[i] = nblk;
         mp.off[i] = (long long)L.coef_offsets[order[i]] * (long long)B;
