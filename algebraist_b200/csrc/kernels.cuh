@@ -1195,43 +1195,54 @@ struct MMParts {
     long long blk0[MM_MAXPARTS + 1];
     long long off[MM_MAXPARTS];
 };
-constexpr int MM_BIG = 128, MM_BIG_K = 8;
+#ifndef SNFFT_MM_BIG_K
+#define SNFFT_MM_BIG_K 16
+#endif
+constexpr int MM_BIG = 128, MM_BIG_K = SNFFT_MM_BIG_K;      // K step of the large tiles: 8 or 16
 __host__ __device__ inline int mm_tile_of(int d, int big_min, bool f32) { return f32 && d >= big_min ? MM_BIG : MM_TILE; }
 
 // fp32, large partitions: a CTA owns a 128 x 128 tile, a thread 8 x 8 outputs as four 4 x 4 blocks (rows ty*4.., 64+ty*4..,
 // columns tx*4.., 64+tx*4..: every operand read is one conflict-free 16-byte shared load, 64 FMA per 4 loads), K in steps
 // of 8, the next K step's global loads issued before the arithmetic of the current one.
+// RH / CH: rows m0 + 64.. / columns n0 + 64.. of the tile exist (edge tiles of a partition skip the arithmetic of an
+// absent half: d = 288 costs 6.25 tile units instead of 9).
+template <bool RH, bool CH>
 __device__ __forceinline__ void block_matmul_big(const float* __restrict__ a, const float* __restrict__ bm, float* __restrict__ c,
                                                  int d, int m0, int n0, float (&As)[MM_BIG_K][MM_BIG + 4],
                                                  float (&Bs)[MM_BIG_K][MM_BIG + 4]) {
+    constexpr int NP = RH ? 4 : 2, NJ = CH ? 8 : 4;        // row pairs and columns this thread accumulates
     const int tid = threadIdx.x;
     const int ty = tid / 16, tx = tid % 16;
-    // loaders: A tile 128 rows x 8 k -> thread (row = tid / 2, k = 4 (tid % 2) ..+3); B tile 8 k x 128 columns -> thread
-    // (k = tid / 32, column = 4 (tid % 32) ..+3).  Scalar loads: d is not a multiple of 4 in general.
-    const int ar = tid / 2, ak = (tid % 2) * 4;
+    // loaders: A tile 128 rows x MM_BIG_K k -> thread (row = tid / 2, k = KH (tid % 2) ..+KH-1, KH = MM_BIG_K / 2); B tile
+    // MM_BIG_K k x 128 columns -> thread (k = tid / 32 + 8 h, column = 4 (tid % 32) ..+3).  Scalar loads: d is not a
+    // multiple of 4 in general.
+    constexpr int KH = MM_BIG_K / 2, NB = MM_BIG_K / 8;
+    const int ar = tid / 2, ak = (tid % 2) * KH;
     const int bk = tid / 32, bc = (tid % 32) * 4;
-    float pa[4], pb[4];
+    float pa[KH], pb[NB][4];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < KH; ++q)
             pa[q] = (m0 + ar < d && k0 + ak + q < d) ? a[(size_t)(m0 + ar) * d + k0 + ak + q] : 0.f;
-            pb[q] = (k0 + bk < d && n0 + bc + q < d) ? bm[(size_t)(k0 + bk) * d + n0 + bc + q] : 0.f;
-        }
+#pragma unroll
+        for (int h = 0; h < NB; ++h)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                pb[h][q] = (k0 + bk + 8 * h < d && n0 + bc + q < d) ? bm[(size_t)(k0 + bk + 8 * h) * d + n0 + bc + q] : 0.f;
     };
-    // accumulators as pairs of ROWS (2p, 2p + 1): one FFMA2 (fma.rn.f32x2) per pair and column, the A operand pairs come
-    // straight out of the 16-byte shared loads, the B operand is duplicated into both halves (8 MOV per 32 FFMA2)
-    F2 acc[4][8];
+    F2 acc[NP][NJ];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NP; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = F2(0.0);
+        for (int j = 0; j < NJ; ++j) acc[i][j] = F2(0.0);
     fetch(0);
     for (int k0 = 0; k0 < d; k0 += MM_BIG_K) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            As[ak + q][ar] = pa[q];
-            Bs[bk][bc + q] = pb[q];
-        }
+        for (int q = 0; q < KH; ++q) As[ak + q][ar] = pa[q];
+#pragma unroll
+        for (int h = 0; h < NB; ++h)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Bs[bk + 8 * h][bc + q] = pb[h][q];
         __syncthreads();
         if (k0 + MM_BIG_K < d) fetch(k0 + MM_BIG_K);
 #pragma unroll
@@ -1240,17 +1251,17 @@ __device__ __forceinline__ void block_matmul_big(const float* __restrict__ a, co
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 av[i] = As[kk][ty * 4 + i];
-                av[4 + i] = As[kk][64 + ty * 4 + i];
+                if (RH) av[4 + i] = As[kk][64 + ty * 4 + i];
                 bv[i] = Bs[kk][tx * 4 + i];
-                bv[4 + i] = Bs[kk][64 + tx * 4 + i];
+                if (CH) bv[4 + i] = Bs[kk][64 + tx * 4 + i];
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 F2 b2;
                 b2.x = bv[j];
                 b2.y = bv[j];
 #pragma unroll
-                for (int pr = 0; pr < 4; ++pr) {
+                for (int pr = 0; pr < NP; ++pr) {
                     F2 a2;
                     a2.x = av[2 * pr];
                     a2.y = av[2 * pr + 1];
@@ -1261,16 +1272,16 @@ __device__ __forceinline__ void block_matmul_big(const float* __restrict__ a, co
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 2 * NP; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4), cc = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
             if (r < d && cc < d) c[(size_t)r * d + cc] = (i & 1) ? acc[i / 2][j].y : acc[i / 2][j].x;
         }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MM_THREADS) block_matmul_kernel(const T* __restrict__ A, const T* __restrict__ B,
+__global__ void __launch_bounds__(MM_THREADS, 2) block_matmul_kernel(const T* __restrict__ A, const T* __restrict__ B,
                                                                   T* __restrict__ C, const MMParts mp) {
     const int tid = threadIdx.x;
     int part = 0;
@@ -1290,7 +1301,14 @@ __global__ void __launch_bounds__(MM_THREADS) block_matmul_kernel(const T* __res
         __shared__ float Ab[MM_BIG_K][MM_BIG + 4];
         __shared__ float Bb[MM_BIG_K][MM_BIG + 4];
         if (tile == MM_BIG) {             // uniform per CTA
-            block_matmul_big((const float*)a, (const float*)bm, (float*)(C + (size_t)b * d * d), d, m0, n0, Ab, Bb);
+            const float* af = (const float*)a;
+            const float* bf = (const float*)bm;
+            float* cf = (float*)(C + (size_t)b * d * d);
+            const bool rh = m0 + 64 < d, ch = n0 + 64 < d;
+            if (rh && ch) block_matmul_big<true, true>(af, bf, cf, d, m0, n0, Ab, Bb);
+            else if (rh) block_matmul_big<true, false>(af, bf, cf, d, m0, n0, Ab, Bb);
+            else if (ch) block_matmul_big<false, true>(af, bf, cf, d, m0, n0, Ab, Bb);
+            else block_matmul_big<false, false>(af, bf, cf, d, m0, n0, Ab, Bb);
             return;
         }
     }
